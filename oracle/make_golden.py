@@ -1,0 +1,210 @@
+"""Test infrastructure (not product): generate tests/golden/*.npz by running
+the UNMODIFIED reference (scikit-gstat 1.0.23 imported from /root/reference,
+see oracle/ref_harness.py) in the build container.
+
+    python oracle/make_golden.py
+
+The GPU box has no /root/reference, so the vectors are committed.  Every
+array is the reference's own output; inputs are stored next to the outputs so
+the parity tests need nothing else.  Case parameters live in a JSON manifest
+inside each npz (key ``manifest``).
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle.fields import gaussian_field, random_points  # noqa: E402
+from oracle.ref_harness import import_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def datasets(skg):
+    ds = {}
+    c, v = skg.data.pancake(N=300, seed=42).get("sample")
+    ds["pancake300"] = (np.asarray(c), np.asarray(v))
+    c = random_points(400, 100.0, 2, seed=1)
+    ds["rnd400"] = (c, gaussian_field(c, 12.0, seed=1))
+    gx, gy = np.meshgrid(np.arange(15), np.arange(15))
+    c = np.column_stack((gx.ravel(), gy.ravel())).astype(float)
+    ds["lattice225"] = (c, gaussian_field(c, 3.0, seed=2))
+    c = random_points(150, 50.0, 3, seed=3)
+    ds["rnd3d150"] = (c, gaussian_field(c, 8.0, seed=3))
+    c = random_points(120, 80.0, 1, seed=4)[:, 0]
+    ds["rnd1d120"] = (c, gaussian_field(c[:, None], 6.0, seed=4))
+    # the reference's own unit-test inputs (tests/test_variogram.py:72-79)
+    np.random.seed(42)
+    c = np.random.gamma(10, 4, (30, 2))
+    np.random.seed(42)
+    v = np.random.normal(10, 4, 30)
+    ds["gamma30"] = (c, v)
+    return ds
+
+
+def make_variogram(skg, ds):
+    arrays, manifest = {}, []
+    lag_cfgs = [(10, None), (25, "median"), (8, "mean"), (6, 0.6), (12, "abs")]
+    for dname, (c, v) in ds.items():
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = v
+        for est in ("matheron", "cressie", "dowd"):
+            for bf in ("even", "uniform"):
+                for n_lags, ml in lag_cfgs:
+                    if ml == "abs":
+                        from scipy.spatial.distance import pdist
+                        cc = c if c.ndim == 2 else np.column_stack((c, np.zeros(len(c))))
+                        ml_val = float(np.round(0.45 * pdist(cc).max(), 3)) + 1.0
+                    else:
+                        ml_val = ml
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        V = skg.Variogram(c, v, estimator=est, bin_func=bf,
+                                          n_lags=n_lags, maxlag=ml_val)
+                    key = "v/%d" % len(manifest)
+                    arrays[key + "/bins"] = V.bins
+                    arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+                    arrays[key + "/experimental"] = V.experimental
+                    arrays[key + "/maxlag"] = np.array(
+                        np.nan if V.maxlag is None else V.maxlag, dtype=float)
+                    arrays[key + "/cof"] = np.asarray(V.cof, dtype=float)
+                    manifest.append(dict(key=key, dataset=dname, estimator=est,
+                                         bin_func=bf, n_lags=n_lags, maxlag=ml_val))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "variogram.npz"), **arrays)
+    print("variogram cases:", len(manifest))
+
+
+def make_directional(skg, ds):
+    arrays, manifest = {}, []
+    dir_cfgs = [
+        dict(azimuth=0, tolerance=45.0, bandwidth="q33", directional_model="triangle"),
+        dict(azimuth=45, tolerance=22.5, bandwidth="q33", directional_model="triangle"),
+        dict(azimuth=-120, tolerance=10.0, bandwidth=30.0, directional_model="triangle"),
+        dict(azimuth=90, tolerance=90.0, bandwidth="q33", directional_model="compass"),
+        dict(azimuth=45, tolerance=22.5, bandwidth="q33", directional_model="compass"),
+        dict(azimuth=170, tolerance=60.0, bandwidth="q50", directional_model="triangle"),
+    ]
+    for dname in ("pancake300", "rnd400", "gamma30"):
+        c, v = ds[dname]
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = v
+        for cfg in dir_cfgs:
+            for bf, est, n_lags, ml in (("even", "matheron", 10, None),
+                                        ("uniform", "matheron", 10, None),
+                                        ("even", "cressie", 8, "median"),
+                                        ("uniform", "dowd", 6, "median")):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    V = skg.DirectionalVariogram(c, v, estimator=est, bin_func=bf,
+                                                 n_lags=n_lags, maxlag=ml, **cfg)
+                key = "d/%d" % len(manifest)
+                arrays[key + "/bins"] = V.bins
+                arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+                arrays[key + "/experimental"] = V.experimental
+                arrays[key + "/maxlag"] = np.array(
+                    np.nan if V.maxlag is None else V.maxlag, dtype=float)
+                arrays[key + "/bandwidth"] = np.array(V.bandwidth, dtype=float)
+                arrays[key + "/mask_count"] = np.array(int(V._direction_mask().sum()))
+                manifest.append(dict(key=key, dataset=dname, estimator=est, bin_func=bf,
+                                     n_lags=n_lags, maxlag=ml, **cfg))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "directional.npz"), **arrays)
+    print("directional cases:", len(manifest))
+
+
+def make_kriging(skg, ds):
+    arrays, manifest = {}, []
+    rng = np.random.default_rng(11)
+    c1000 = random_points(1000, 500.0, 2, seed=5)
+    local = dict(ds)
+    local["rnd1000"] = (c1000, gaussian_field(c1000, 60.0, seed=5))
+    c3 = random_points(400, 60.0, 3, seed=6)
+    local["rnd3d400"] = (c3, gaussian_field(c3, 12.0, seed=6))
+    cases = [
+        dict(dataset="pancake300", model="exponential", n_lags=25, maxlag="median",
+             min_points=5, max_points=64, targets="grid6"),
+        dict(dataset="pancake300", model="spherical", n_lags=10, maxlag=None,
+             min_points=5, max_points=15, targets="rand120+samples"),
+        dict(dataset="rnd1000", model="exponential", n_lags=25, maxlag="median",
+             min_points=5, max_points=64, targets="rand300"),
+        dict(dataset="rnd1000", model="spherical", n_lags=20, maxlag=0.3,
+             min_points=8, max_points=20, targets="rand300far"),
+        dict(dataset="rnd1000", model="cubic", n_lags=20, maxlag="median",
+             min_points=3, max_points=12, targets="rand200"),
+        # stable with a manual shape: the free fit runs into shape=2 (Gaussian-like,
+        # cond(A) ~ 1e18, no meaningful parity - SURVEY.md section 7.3 item 4)
+        dict(dataset="rnd1000", model="stable", n_lags=20, maxlag="median",
+             min_points=3, max_points=24, targets="rand200",
+             manual=dict(fit_range=150.0, fit_sill=3.5, fit_shape=1.3)),
+        dict(dataset="rnd1000", model="exponential", n_lags=25, maxlag="median",
+             min_points=5, max_points=32, targets="rand200", use_nugget=True),
+        dict(dataset="rnd3d400", model="exponential", n_lags=15, maxlag="median",
+             min_points=4, max_points=16, targets="rand150"),
+        dict(dataset="lattice225", model="spherical", n_lags=8, maxlag=None,
+             min_points=4, max_points=10, targets="latticehalf"),
+    ]
+    for case in cases:
+        c, v = local[case["dataset"]]
+        arrays["in/%s/coords" % case["dataset"]] = c
+        arrays["in/%s/values" % case["dataset"]] = v
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            extra = {}
+            if "manual" in case:
+                extra = dict(fit_method="manual", **case["manual"])
+            V = skg.Variogram(c, v, model=case["model"], n_lags=case["n_lags"],
+                              maxlag=case["maxlag"],
+                              use_nugget=case.get("use_nugget", False), **extra)
+        lo, hi = c.min(axis=0), c.max(axis=0)
+        dim = c.shape[1]
+        kind = case["targets"]
+        if kind == "grid6":
+            t = np.mgrid[0:499:6j, 0:499:6j].reshape(2, -1).T
+        elif kind == "rand120+samples":
+            t = np.vstack((lo + rng.random((120, dim)) * (hi - lo), c[:15].astype(float)))
+        elif kind == "rand300far":
+            t = lo - 0.4 * (hi - lo) + rng.random((300, dim)) * 1.8 * (hi - lo)
+        elif kind == "latticehalf":
+            gx, gy = np.meshgrid(np.arange(-1, 16, 0.5), np.arange(-1, 16, 0.5))
+            t = np.column_stack((gx.ravel(), gy.ravel()))
+        else:
+            t = lo + rng.random((int(kind[4:]), dim)) * (hi - lo)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ok = skg.OrdinaryKriging(V, min_points=case["min_points"],
+                                     max_points=case["max_points"])
+            z = ok.transform(*[t[:, k] for k in range(dim)])
+        d = V.describe()
+        key = "k/%d" % len(manifest)
+        arrays[key + "/targets"] = t
+        arrays[key + "/z"] = z
+        arrays[key + "/sigma"] = ok.sigma
+        entry = dict(case)
+        entry.update(key=key, effective_range=float(d["effective_range"]),
+                     sill=float(d["sill"]), nugget=float(d["nugget"]),
+                     shape=(float(d["shape"]) if "shape" in d else None),
+                     no_points_error=int(ok.no_points_error),
+                     singular_error=int(ok.singular_error))
+        manifest.append(entry)
+        print(key, case["dataset"], case["model"], "nan:", int(np.isnan(z).sum()), "of", len(z))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "kriging.npz"), **arrays)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    skg = import_reference()
+    ds = datasets(skg)
+    make_variogram(skg, ds)
+    make_directional(skg, ds)
+    make_kriging(skg, ds)
+
+
+if __name__ == "__main__":
+    main()

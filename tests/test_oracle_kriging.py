@@ -1,0 +1,36 @@
+"""CPU: pin the kriging oracle against reference outputs (tests/golden/kriging.npz).
+The reference's own tests hold no numeric kriging goldens,
+so the live-reference vectors are the only pin."""
+import numpy as np
+from numpy.testing import assert_allclose, assert_array_equal
+
+from oracle import kriging as ok
+
+
+def test_kriging_oracle_matches_reference_golden(golden_kriging):
+    g = golden_kriging
+    for case in g.manifest:
+        c, v = g.inputs(case["dataset"])
+        t = g.out(case, "targets")
+        z, sigma, status = ok.krige(
+            c, v, t, case["model"], case["effective_range"], case["sill"], case["nugget"],
+            case["shape"], case["min_points"], case["max_points"])
+        zr, sr = g.out(case, "z"), g.out(case, "sigma")
+        assert_array_equal(np.isnan(z), np.isnan(zr), err_msg=str(case))
+        assert_array_equal(np.isnan(sigma), np.isnan(sr), err_msg=str(case))
+        assert int((status == 1).sum()) == case["no_points_error"]
+        # the reference evaluates the model through numba scalar calls, the oracle
+        # through numpy ufuncs: last-bit differences amplified by cond(A) ~ 1e3..1e5
+        assert_allclose(z, zr, rtol=1e-9, equal_nan=True, err_msg=str(case))
+        assert_allclose(sigma, sr, rtol=1e-9, atol=1e-9 * case["sill"], equal_nan=True,
+                        err_msg=str(case))
+
+
+def test_pancake_kriging_known_answer(golden_kriging):
+    """BASELINE.md section 3."""
+    g = golden_kriging
+    case = g.manifest[0]
+    assert_allclose(g.out(case, "z")[:4], [216.82668695078203, 213.25019510789258,
+                                           208.75398093840414, 204.76546428916612], rtol=1e-12)
+    assert_allclose(g.out(case, "sigma")[:4], [821.5990160593558, 607.4358198357556,
+                                               457.6864840412478, 250.3293362582594], rtol=1e-12)
