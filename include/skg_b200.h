@@ -1,0 +1,224 @@
+/*
+ * skg_b200.h - C ABI of the B200-native (sm_100a) experimental-variogram and
+ * ordinary-kriging hot path.  This is the drop-in boundary: everything the
+ * reference (scikit-gstat 1.0.23, pure Python) computes on this path through
+ * scipy/numpy/numba is replaced by the entry points below.  Host code (Python,
+ * scikit-gstat_b200/skgstat_b200/_lib.py) binds them with ctypes; a reference
+ * maintainer would add the same ctypes stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types in any signature.
+ *   - pointers marked [dev] are device pointers on the current CUDA device
+ *     (e.g. torch.Tensor.data_ptr()); [host] pointers are ordinary host memory
+ *     and are consumed before the call returns.
+ *   - coordinates are fp64 struct-of-arrays: coords[k*n + i] = k-th coordinate
+ *     of point i, dim in {2, 3} (1-D input gets a zero column appended by the
+ *     caller, as Variogram.py:291-297 does).
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream); no implicit synchronisation, no
+ *     persistent allocation, no global state besides the last-error string.
+ *   - the caller owns all buffers, including scratch.  Accumulating outputs
+ *     must be zero-initialised by the caller unless stated otherwise.
+ *   - return value: 0 ok, <0 invalid argument (SKG_E_*), >0 a cudaError_t.
+ *     Never throws, never aborts.  skg_last_error() describes the last failure
+ *     of the calling thread.
+ *   - the pair triangle is cut into SKG_TILE x SKG_TILE point tiles (upper
+ *     triangle incl. diagonal, row-major linearised).  [tile_begin, tile_end)
+ *     selects a sub-range, which is how the sweep is sharded across GPUs.
+ *
+ * Squared-distance space.  Per pair the kernels compute
+ *     s = fl(fl(dx*dx) + fl(dy*dy)) [ + fl(dz*dz) ]     (no FMA)
+ * which is the operand scipy's euclidean kernel hands to sqrt
+ * (MetricSpace.py:151-153 -> scipy pdist).  IEEE sqrt is monotone and
+ * correctly rounded, so `d >= e` <=> `s >= T(e)` with
+ * T(e) = min{ s : fl(sqrt(s)) >= e }.  Lag-class edges are therefore passed
+ * as the BIT PATTERNS of T(e_k) (uint64, monotone for non-negative doubles) and
+ * compared as integers: np.digitize(d, edges) (Variogram.py:2005) is reproduced
+ * exactly with no sqrt in the hot loop.
+ */
+#ifndef SKG_B200_H
+#define SKG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKG_ABI_VERSION 1
+#define SKG_TILE 256            /* points per tile edge                          */
+#define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
+#define SKG_KRIGE_MAX_POINTS 64 /* max_points supported by the warp-per-target kernel */
+
+/* error codes (<0) */
+#define SKG_E_BADARG (-1)
+#define SKG_E_UNSUPPORTED (-2)
+#define SKG_E_NODEVICE (-3)
+#define SKG_E_SCRATCH (-4)
+
+/* directional model ids (DirectionalVariogram.py:522-575) */
+#define SKG_DIR_NONE 0
+#define SKG_DIR_TRIANGLE 1 /* DirectionalVariogram._triangle :659-714 */
+#define SKG_DIR_COMPASS 2  /* DirectionalVariogram._compass  :749-782 */
+
+/* estimator statistic flags for skg_pair_hist */
+#define SKG_STAT_SUM_SQ 1   /* sum (dz)^2     - estimators.matheron :66   */
+#define SKG_STAT_SUM_SQRT 2 /* sum |dz|^(1/2) - estimators.cressie  :123  */
+
+/* key kinds for the select passes */
+#define SKG_KEY_SQDIST 0 /* s = squared distance (order statistics of d)       */
+#define SKG_KEY_ABSDZ 1  /* |z_i - z_j|        (Dowd per-lag median)            */
+
+/* theoretical models for kriging (models.py) */
+#define SKG_MODEL_SPHERICAL 0   /* models.py:21-82   */
+#define SKG_MODEL_EXPONENTIAL 1 /* models.py:85-144  */
+#define SKG_MODEL_GAUSSIAN 2    /* models.py:147-209 */
+#define SKG_MODEL_CUBIC 3       /* models.py:212-272 */
+#define SKG_MODEL_STABLE 4      /* models.py:275-344 */
+
+/* kriging per-target status (Kriging.py:25-38, 492-513) */
+#define SKG_KRIGE_OK 0
+#define SKG_KRIGE_LESS_POINTS 1 /* LessPointsError  -> z = sigma = NaN */
+#define SKG_KRIGE_SINGULAR 2    /* SingularMatrixError -> NaN          */
+
+int skg_abi_version(void);
+const char* skg_last_error(void);
+
+/* Number of SMs of the current device (grid sizing is internal; exposed for
+ * reporting) and a DFMA-chain microbenchmark used as the FP64 roofline
+ * denominator (MEASURED_PEAKS.json has no FP64 figure).  skg_fp64_peak runs
+ * `iters` dependent-chain DFMA batches on every SM and returns the elapsed
+ * kernel time in ms through *ms and the number of FP64 FMA executed through
+ * *fma_count (flops = 2 * fma_count).  Synchronous. */
+int skg_device_sm_count(int* sm_count);
+int skg_fp64_peak(int iters, double* ms, double* fma_count);
+
+/* Number of SKG_TILE tiles in the pair triangle of n points. */
+int64_t skg_pair_num_tiles(int64_t n);
+
+/* Directional mask parameters [host, 5 doubles] or NULL for the isotropic case:
+ *   dir[0] = model id (SKG_DIR_*), dir[1] = np.radians(azimuth),
+ *   dir[2] = np.radians(tolerance / 2), dir[3] = bandwidth / 2,
+ *   dir[4] = guard-band policy (below)
+ * exactly the quantities DirectionalVariogram._triangle/_compass compare
+ * against.  Pair vector is P_i - P_j for i < j (pdist order,
+ * DirectionalVariogram.py:404-413).  2-D coordinates only (as the reference).
+ *
+ * The kernels decide the mask without transcendentals (dot/cross products
+ * against the azimuth direction).  The reference decides it through
+ * arccos/sin of its host libm (DirectionalVariogram.py:405, 712), so pairs that
+ * lie within a relative 2^-40 of a decision boundary (exact geometric ties on
+ * lattice data; none on generic float data) are libm-dependent.  Policy
+ *   dir[4] = 0: such pairs are decided by the literal formula with the CUDA libm;
+ *   dir[4] = 1: such pairs FAIL the mask in every kernel; the caller lists them
+ *               once with skg_pair_dir_ambiguous, decides them with the literal
+ *               numpy formula on the host (the reference's own arithmetic) and
+ *               adds their contributions.  This is what skgstat_b200 does. */
+int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const double* dir,
+                           int32_t* pair_i, int32_t* pair_j, uint64_t* count, int64_t capacity,
+                           int64_t tile_begin, int64_t tile_end, void* stream);
+
+/* K2 - fused distance -> lag class -> estimator statistics.
+ * Replaces MetricSpace.dists + Variogram.distance + _calc_diff + _calc_groups
+ * + lag_classes + estimators.matheron/cressie (MetricSpace.py:135-156,
+ * Variogram.py:1202-1208, 1938-2006, 1535-1557, 2092; estimators.py:14-128).
+ *   thr_bits [host, n_lags]  bit patterns of T(edge_k), non-decreasing
+ *   count    [dev, n_lags]   += pairs per lag class (exact)
+ *   sum_sq   [dev, n_lags]   += sum dz^2          (if stats & SKG_STAT_SUM_SQ)
+ *   sum_sqrt [dev, n_lags]   += sum sqrt|dz|      (if stats & SKG_STAT_SUM_SQRT)
+ *   scratch  [dev]           >= skg_pair_hist_scratch_bytes(n_lags) bytes
+ * Per-CTA partials are reduced in a fixed order: results are run-to-run
+ * reproducible for a given (n, tile range). */
+int64_t skg_pair_hist_scratch_bytes(int n_lags);
+int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim,
+                  const double* dir, const uint64_t* thr_bits, int n_lags, int stats,
+                  uint64_t* count, double* sum_sq, double* sum_sqrt,
+                  void* scratch, int64_t scratch_bytes,
+                  int64_t tile_begin, int64_t tile_end, void* stream);
+
+/* K1/K3 - histogram pass of the exact order-statistic search.
+ * Replaces np.nanmax / np.median / np.percentile / np.nanpercentile over the
+ * condensed distance vector (binning.py:37-40, 70-79; Variogram.py:1288-1293;
+ * DirectionalVariogram.py:509) and np.nanmedian per lag class
+ * (estimators.py:178) without materialising anything.
+ * Segments: n_lags == 0 -> one segment holding every (mask-passing) pair;
+ *           n_lags  > 0 -> segment = lag class of the pair (thr_bits as in K2).
+ * Key: SKG_KEY_SQDIST or SKG_KEY_ABSDZ.  A key v of segment g is counted iff
+ *   lo_bits[g] <= bits(v) < hi_bits[g]; its bucket is
+ *   min(n_buckets-1, trunc(fl(fl(v - lo[g]) * scale[g])))   (no FMA; monotone in v)
+ *   seg_lo_bits/seg_hi_bits [host, nseg] uint64, seg_scale [host, nseg] double
+ *   hist     [dev, nseg*n_buckets] uint64 += counts
+ *   max_bits [dev, 1] uint64 atomicMax of the key bits over ALL mask-passing
+ *            pairs (window ignored); only written when n_lags == 0; may be NULL.
+ */
+int skg_pair_select_hist(const double* coords, const double* values, int64_t n, int dim,
+                         const double* dir, const uint64_t* thr_bits, int n_lags,
+                         int key_kind, const uint64_t* seg_lo_bits,
+                         const uint64_t* seg_hi_bits, const double* seg_scale,
+                         int64_t n_buckets, uint64_t* hist, uint64_t* max_bits,
+                         int64_t tile_begin, int64_t tile_end, void* stream);
+
+/* Gather pass: every key whose (segment, bucket) bit is set in `bitmap`
+ * ([dev] uint32 words, bit index = g*n_buckets + bucket) is appended to
+ * cand_key / cand_slot (slot = g*n_buckets + bucket).  cand_count [dev,1]
+ * counts all hits, also those beyond `capacity` (which are dropped; the caller
+ * then refines the window and repeats).  Order of candidates is unspecified. */
+int skg_pair_select_gather(const double* coords, const double* values, int64_t n, int dim,
+                           const double* dir, const uint64_t* thr_bits, int n_lags,
+                           int key_kind, const uint64_t* seg_lo_bits,
+                           const uint64_t* seg_hi_bits, const double* seg_scale,
+                           int64_t n_buckets, const uint32_t* bitmap,
+                           double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
+                           int64_t capacity,
+                           int64_t tile_begin, int64_t tile_end, void* stream);
+
+/* Materialising accessors (Variogram.distance :1202, pairwise_diffs :592-606,
+ * lag_groups :1514-1533, DirectionalVariogram._direction_mask :605-624) for the
+ * condensed pair range [pair_begin, pair_end), k = n*i - i(i+1)/2 + (j-i-1).
+ * Any output may be NULL.  dist = fl(sqrt(s)) (bit-identical to scipy pdist),
+ * diffs = |z_i - z_j|, groups = lag class or -1, mask = 1/0. */
+int skg_pair_materialize(const double* coords, const double* values, int64_t n, int dim,
+                         const double* dir, const uint64_t* thr_bits, int n_lags,
+                         double* dist, double* diffs, int64_t* groups, uint8_t* mask,
+                         int64_t pair_begin, int64_t pair_end, void* stream);
+
+/* K5 - batched ordinary kriging (OrdinaryKriging.transform, Kriging.py:405-650;
+ * find_closest MetricSpace.py:26-71; models.py).
+ *
+ * Step 1, once per sample set: bucket the samples into a uniform cell grid.
+ *   grid [host, 8 doubles]: origin x,y,z ; cell edge h ; nx, ny, nz ; unused
+ *   cell_start [dev, ncell+1] int32 (out), order [dev, n] int32 (out):
+ *   order[cell_start[c] .. cell_start[c+1]) = sample ids of cell c, ascending.
+ *   scratch [dev] >= (ncell + n) * 4 bytes.
+ */
+int skg_krige_build_grid(const double* coords, int64_t n, int dim, const double* grid,
+                         int32_t* cell_start, int32_t* order,
+                         void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Step 2: one warp per target.  For target t: neighbours = samples with
+ * d <= radius; if more than max_points, the max_points smallest by
+ * (d, sample id) (stable argsort, MetricSpace.py:64-70); fewer than min_points
+ * -> status LESS_POINTS, NaN.  System: A_ij = gamma(d_ij) (i != j), A_ii = 0,
+ * border 1, corner 0; b_i = gamma(d_0i), b_n = 1 (Kriging.py:594-614); solved
+ * by partial-pivot LU in fp64; sigma = sum(w_i b_i) + lambda, z = w . values
+ * (Kriging.py:644-647).
+ *   model_params [host, 4 doubles]: range r, sill c0, shape s (stable only),
+ *                nugget b (0 = none) - the cof of Variogram.fitted_model_function
+ *   targets [dev, dim*m] SoA; z, sigma [dev, m] (out); status [dev, m] int32 (out)
+ *   scratch [dev] >= skg_krige_scratch_bytes(max_points) bytes
+ *   [target_begin, target_end) sub-range (multi-GPU sharding; outputs indexed
+ *   by absolute target id).
+ */
+int64_t skg_krige_scratch_bytes(int max_points);
+int skg_krige(const double* coords, const double* values, int64_t n, int dim,
+              const double* grid, const int32_t* cell_start, const int32_t* order,
+              const double* targets, int64_t m, int model, const double* model_params,
+              double radius, int min_points, int max_points,
+              double* z, double* sigma, int32_t* status,
+              void* scratch, int64_t scratch_bytes,
+              int64_t target_begin, int64_t target_end, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKG_B200_H */

@@ -1,0 +1,632 @@
+// K5: batched ordinary kriging for sm_100a - one warp per target point.
+//
+// Restates OrdinaryKriging.transform (Kriging.py:405-650) for mode='exact':
+//   neighbour search  = MetricSpacePair.find_closest (MetricSpace.py:26-71):
+//                       d <= radius, the max_points smallest by (d, sample id);
+//   system            = Kriging.py:594-614 (gamma off-diagonal, 0 diagonal,
+//                       unit border, zero corner; rhs gamma(d_0i), 1);
+//   solve             = partial-pivot LU in fp64 (the reference multiplies by
+//                       numpy.linalg.inv, i.e. LAPACK dgetrf/dgetri);
+//   outputs           = Kriging.py:644-647.
+// The M x N target-sample distance matrix (MetricSpace.py:248-253) and the
+// N x N sample matrix (MetricSpace.py:158-187) are never formed: samples are
+// bucketed in a uniform cell grid and each warp expands Chebyshev rings of
+// cells around its target until the max_points nearest are provably inside.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace skg {
+
+struct GridParams {
+  double ox, oy, oz, h;
+  int nx, ny, nz;
+};
+
+struct ModelParams {
+  int model;
+  double r, c0, s, b;
+  double a;  // derived range parameter (models.py: r/1, r/3, r/2, r/3^(1/s))
+};
+
+__device__ __forceinline__ int cell_coord(double p, double o, double inv_h) {
+  double f = floor((p - o) * inv_h);
+  f = fmin(fmax(f, -1.0e9), 1.0e9);
+  return (int)f;
+}
+
+// ------------------------------------------------------------ grid build ---
+
+template <int DIM>
+__global__ void grid_count_kernel(const double* __restrict__ coords, int64_t n, GridParams g,
+                                  int* __restrict__ cellid, int* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double inv_h = 1.0 / g.h;
+  int cx = min(max(cell_coord(coords[i], g.ox, inv_h), 0), g.nx - 1);
+  int cy = min(max(cell_coord(coords[n + i], g.oy, inv_h), 0), g.ny - 1);
+  int cz = 0;
+  if (DIM == 3) cz = min(max(cell_coord(coords[2 * n + i], g.oz, inv_h), 0), g.nz - 1);
+  const int c = (cz * g.ny + cy) * g.nx + cx;
+  cellid[i] = c;
+  atomicAdd(&counts[c], 1);
+}
+
+// single-CTA exclusive scan: cell_start[0..ncell], cursor[c] = cell_start[c]
+__global__ void grid_scan_kernel(int* __restrict__ counts, int ncell, int* __restrict__ cell_start) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < ncell; base += blockDim.x) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < ncell ? counts[idx] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int before = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
+    if (idx < ncell) {
+      cell_start[idx] = before;
+      counts[idx] = before;  // becomes the scatter cursor
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cell_start[ncell] = carry;
+}
+
+__global__ void grid_scatter_kernel(const int* __restrict__ cellid, int64_t n,
+                                    int* __restrict__ cursor, int* __restrict__ order) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int pos = atomicAdd(&cursor[cellid[i]], 1);
+  order[pos] = (int)i;
+}
+
+// deterministic order inside each cell: ascending sample id
+__global__ void grid_sort_cells_kernel(const int* __restrict__ cell_start, int ncell,
+                                       int* __restrict__ order) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int a = cell_start[c], b = cell_start[c + 1];
+  for (int i = a + 1; i < b; ++i) {
+    const int v = order[i];
+    int j = i - 1;
+    while (j >= a && order[j] > v) {
+      order[j + 1] = order[j];
+      --j;
+    }
+    order[j + 1] = v;
+  }
+}
+
+// ---------------------------------------------------------------- models ---
+
+__device__ __forceinline__ double gamma_model(double h, const ModelParams& m) {
+  switch (m.model) {
+    case SKG_MODEL_SPHERICAL: {  // models.py:77-82
+      if (h <= m.r) {
+        const double q = h / m.a;
+        return m.b + m.c0 * ((1.5 * q) - (0.5 * (q * q * q)));
+      }
+      return m.b + m.c0;
+    }
+    case SKG_MODEL_EXPONENTIAL:  // models.py:142-144
+      return m.b + m.c0 * (1.0 - exp(-(h / m.a)));
+    case SKG_MODEL_GAUSSIAN:  // models.py:207-209
+      return m.b + m.c0 * (1.0 - exp(-((h * h) / (m.a * m.a))));
+    case SKG_MODEL_CUBIC: {  // models.py:264-272
+      if (h < m.r) {
+        const double a2 = m.a * m.a, h2 = h * h;
+        const double a3 = a2 * m.a, h3 = h2 * h;
+        const double a5 = a3 * a2, h5 = h3 * h2;
+        const double a7 = a5 * a2, h7 = h5 * h2;
+        return m.b + m.c0 * ((7.0 * (h2 / a2)) - (8.75 * (h3 / a3)) + (3.5 * (h5 / a5)) -
+                             (0.75 * (h7 / a7)));
+      }
+      return m.b + m.c0;
+    }
+    default: {  // stable, models.py:336-344
+      if (h == 0.0) return m.b;
+      return m.b + m.c0 * (1.0 - exp(-pow(h / m.a, m.s)));
+    }
+  }
+}
+
+// ------------------------------------------------------------ the kernel ---
+
+struct KrigeArgs {
+  const double* coords;
+  const double* values;
+  int64_t n;
+  GridParams grid;
+  const int* cell_start;
+  const int* order;
+  const double* targets;
+  int64_t m;
+  ModelParams model;
+  double radius;
+  int min_points, max_points;
+  double* z;
+  double* sigma;
+  int* status;
+  int64_t t0, t1;
+  int cap;           // candidate list capacity per warp
+  int region_bytes;  // per-warp shared region (list, later the matrix)
+};
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// Keep the k smallest (key, id) of the warp's list; returns new length (k).
+// Bisection on the key bit pattern, ties on the k-th key broken by ascending
+// sample id (np.argsort(kind='stable') on index-ordered input, MetricSpace.py:69).
+__device__ int prune_list(unsigned long long* keys, int* ids, int len, int k, int lane) {
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (int e = lane; e < len; e += 32) {
+    const unsigned long long v = keys[e];
+    lo = v < lo ? v : lo;
+    hi = v > hi ? v : hi;
+  }
+  lo = warp_min_u64(lo);
+  hi = warp_max_u64(hi);
+  bool exact = false;
+  unsigned long long T = hi;
+  while (lo < hi) {
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+    for (int e = lane; e < len; e += 32) c += keys[e] <= mid ? 1 : 0;
+    c = warp_sum_int(c);
+    if (c == k) { T = mid; exact = true; break; }
+    if (c > k) hi = mid; else lo = mid + 1;
+  }
+  int idcut = 0x7fffffff;
+  if (!exact) {
+    T = lo;
+    int below = 0;
+    for (int e = lane; e < len; e += 32) below += keys[e] < T ? 1 : 0;
+    below = warp_sum_int(below);
+    const int need = k - below;  // >= 1 ties to take, smallest ids first
+    int ilo = 0, ihi = 0x7fffffff;
+    while (ilo < ihi) {
+      const int mid = ilo + ((ihi - ilo) >> 1);
+      int c = 0;
+      for (int e = lane; e < len; e += 32) c += (keys[e] == T && ids[e] <= mid) ? 1 : 0;
+      c = warp_sum_int(c);
+      if (c >= need) ihi = mid; else ilo = mid + 1;
+    }
+    idcut = ilo;
+  }
+  // stable in-place compaction (reads of a chunk complete before its writes; writes
+  // only go to positions <= the chunk's first read position)
+  int out = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int e = base + lane;
+    unsigned long long v = 0ull;
+    int id = 0;
+    bool keep = false;
+    if (e < len) {
+      v = keys[e];
+      id = ids[e];
+      keep = (v < T) || (v == T && (exact || id <= idcut));
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) {
+      const int pos = out + __popc(mask & ((1u << lane) - 1u));
+      keys[pos] = v;
+      ids[pos] = id;
+    }
+    out += __popc(mask);
+    __syncwarp();
+  }
+  return out;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+krige_kernel(const __grid_constant__ KrigeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int maxp = a.max_points;
+  // per-warp layout: region | nbr coords [DIM][maxp] | nbr values [maxp] | rhs copy [maxp+1] | mult [maxp+1]
+  const int per_warp = a.region_bytes + (DIM + 1) * maxp * 8 + 2 * (maxp + 1) * 8;
+  unsigned char* base = smem_raw + (size_t)warp * per_warp;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  int* ids = reinterpret_cast<int*>(base + (size_t)a.cap * 8);
+  double* A = reinterpret_cast<double*>(base);
+  double* ncoord = reinterpret_cast<double*>(base + a.region_bytes);
+  double* nval = ncoord + DIM * maxp;
+  double* rhs = nval + maxp;
+  double* mult = rhs + (maxp + 1);
+
+  const double* __restrict__ X = a.coords;
+  const double* __restrict__ Y = a.coords + a.n;
+  const double* __restrict__ W = a.coords + 2 * a.n;
+  const GridParams g = a.grid;
+  const double inv_h = 1.0 / g.h;
+  const int rmax = (int)ceil(a.radius * inv_h) + 1;
+  const double qnan = __longlong_as_double(NAN_BITS);
+
+  for (int64_t t = a.t0 + (int64_t)blockIdx.x * wpb + warp; t < a.t1; t += (int64_t)gridDim.x * wpb) {
+    const double tx = a.targets[t];
+    const double ty = a.targets[a.m + t];
+    const double tw = DIM == 3 ? a.targets[2 * a.m + t] : 0.0;
+    const int cx = cell_coord(tx, g.ox, inv_h);
+    const int cy = cell_coord(ty, g.oy, inv_h);
+    const int cz = DIM == 3 ? cell_coord(tw, g.oz, inv_h) : 0;
+    int len = 0;
+    double rad = a.radius;  // shrinks to the k-th distance after a prune
+    // rings that can contain anything: up to the farthest grid cell
+    int far = max(max(cx, g.nx - 1 - cx), max(cy, g.ny - 1 - cy));
+    if (DIM == 3) far = max(far, max(cz, g.nz - 1 - cz));
+    const int rstop = min(rmax, max(far, 0));
+    bool nan_target = !(tx == tx) || !(ty == ty) || (DIM == 3 && !(tw == tw));
+
+    for (int r = 0; r <= rstop && !nan_target; ++r) {
+      const int z0 = DIM == 3 ? cz - r : 0, z1 = DIM == 3 ? cz + r : 0;
+      for (int zz = z0; zz <= z1; ++zz) {
+        if (zz < 0 || zz >= g.nz) continue;
+        const bool zface = DIM == 3 && (zz == cz - r || zz == cz + r);
+        for (int yy = cy - r; yy <= cy + r; ++yy) {
+          if (yy < 0 || yy >= g.ny) continue;
+          const bool full_row = zface || yy == cy - r || yy == cy + r;
+          // full row: cells cx-r..cx+r (one contiguous run); else only cx-r and cx+r
+          const int nruns = full_row ? 1 : (r == 0 ? 1 : 2);
+          for (int run = 0; run < nruns; ++run) {
+            int xa, xb;
+            if (full_row) { xa = cx - r; xb = cx + r; }
+            else { xa = xb = (run == 0 ? cx - r : cx + r); }
+            xa = max(xa, 0);
+            xb = min(xb, g.nx - 1);
+            if (xa > xb) continue;
+            const int rowbase = (zz * g.ny + yy) * g.nx;
+            const int s0 = a.cell_start[rowbase + xa];
+            const int s1 = a.cell_start[rowbase + xb + 1];
+            for (int sb = s0; sb < s1; sb += 32) {
+              if (len + 32 > a.cap) {  // make room: keep the best max_points so far
+                __syncwarp();
+                len = prune_list(keys, ids, len, maxp, lane);
+                unsigned long long kmax = 0ull;
+                for (int e = lane; e < len; e += 32) kmax = keys[e] > kmax ? keys[e] : kmax;
+                kmax = warp_max_u64(kmax);
+                rad = fmin(rad, __longlong_as_double((long long)kmax));
+                __syncwarp();
+              }
+              const int sidx = sb + lane;
+              bool hit = false;
+              double d = 0.0;
+              int id = 0;
+              if (sidx < s1) {
+                id = a.order[sidx];
+                const double dx = tx - X[id];
+                const double dy = ty - Y[id];
+                double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (DIM == 3) {
+                  const double dw = tw - W[id];
+                  s = __dadd_rn(s, __dmul_rn(dw, dw));
+                }
+                d = sqrt(s);  // cdist value, MetricSpace.py:248-253
+                hit = d <= rad;  // MetricSpace.py:61
+              }
+              const unsigned mask = __ballot_sync(0xffffffffu, hit);
+              if (hit) {
+                const int pos = len + __popc(mask & ((1u << lane) - 1u));
+                keys[pos] = (unsigned long long)__double_as_longlong(d);
+                ids[pos] = id;
+              }
+              len += __popc(mask);
+            }
+          }
+        }
+      }
+      // everything within r*h of the target has been seen after ring r
+      __syncwarp();
+      if (len >= maxp) {
+        const double safe = (double)r * g.h * (1.0 - 9.5367431640625e-07);
+        int c = 0;
+        for (int e = lane; e < len; e += 32)
+          c += __longlong_as_double((long long)keys[e]) <= safe ? 1 : 0;
+        c = warp_sum_int(c);
+        if (c >= maxp) break;
+      }
+    }
+    __syncwarp();
+    if (len > maxp) len = prune_list(keys, ids, len, maxp, lane);
+    __syncwarp();
+    const int nn = len;
+    if (nn < a.min_points || nn < 1) {  // Kriging.py:579-580 LessPointsError
+      if (lane == 0) {
+        a.z[t] = qnan;
+        a.sigma[t] = qnan;
+        a.status[t] = SKG_KRIGE_LESS_POINTS;
+      }
+      __syncwarp();
+      continue;
+    }
+    // pull the neighbours out of the list region before it becomes the matrix
+    double kd[2];
+    int kid[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      kd[q] = e < nn ? __longlong_as_double((long long)keys[e]) : 0.0;
+      kid[q] = e < nn ? ids[e] : 0;
+    }
+    __syncwarp();
+    const int N = nn + 1;   // system size
+    const int LD = (N + 1) | 1;  // augmented with the rhs column (index N); odd stride keeps column walks bank-conflict free
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      if (e < nn) {
+        ncoord[e] = X[kid[q]];
+        ncoord[maxp + e] = Y[kid[q]];
+        if (DIM == 3) ncoord[2 * maxp + e] = W[kid[q]];
+        nval[e] = a.values[kid[q]];
+        const double gv = gamma_model(kd[q], a.model);  // Kriging.py:611-613
+        rhs[e] = gv;
+        A[e * LD + N] = gv;
+        A[e * LD + e] = 0.0;       // squareform diagonal, Kriging.py:600
+        A[e * LD + nn] = 1.0;      // Kriging.py:601
+        A[nn * LD + e] = 1.0;      // Kriging.py:602
+      }
+    }
+    if (lane == 0) {
+      A[nn * LD + nn] = 0.0;  // Kriging.py:604
+      A[nn * LD + N] = 1.0;
+      rhs[nn] = 1.0;
+    }
+    __syncwarp();
+    const int npairs = nn * (nn - 1) / 2;
+    for (int p = lane; p < npairs; p += 32) {
+      // p -> (i, j), i < j, row-major upper triangle
+      int i = (int)((2.0 * nn - 1.0 - sqrt((2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * p)) * 0.5);
+      while (i > 0 && i * nn - i * (i + 1) / 2 > p) --i;
+      while ((i + 1) * nn - (i + 1) * (i + 2) / 2 <= p) ++i;
+      const int j = p - (i * nn - i * (i + 1) / 2) + i + 1;
+      const double dx = ncoord[i] - ncoord[j];
+      const double dy = ncoord[maxp + i] - ncoord[maxp + j];
+      double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      if (DIM == 3) {
+        const double dw = ncoord[2 * maxp + i] - ncoord[2 * maxp + j];
+        s = __dadd_rn(s, __dmul_rn(dw, dw));
+      }
+      const double gv = gamma_model(sqrt(s), a.model);  // Kriging.py:594, 652-654
+      A[i * LD + j] = gv;
+      A[j * LD + i] = gv;
+    }
+    __syncwarp();
+
+    // ---- partial-pivot Gaussian elimination on [A | b] -------------------
+    bool singular = false;
+    for (int k = 0; k < N; ++k) {
+      double best = -1.0;
+      int brow = k;
+      for (int i = k + lane; i < N; i += 32) {
+        const double v = fabs(A[i * LD + k]);
+        if (v > best) { best = v; brow = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+        if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+      }
+      if (!(best > 0.0)) { singular = true; break; }  // zero (or NaN) pivot column
+      if (brow != k) {
+        for (int j = k + lane; j < LD; j += 32) {
+          const double u = A[k * LD + j];
+          A[k * LD + j] = A[brow * LD + j];
+          A[brow * LD + j] = u;
+        }
+      }
+      __syncwarp();
+      const double rp = 1.0 / A[k * LD + k];
+      for (int i = k + 1 + lane; i < N; i += 32) mult[i] = A[i * LD + k] * rp;
+      __syncwarp();
+      // rank-1 update of the trailing block, lanes over columns
+      const int ncol = LD - (k + 1);
+      for (int jb = 0; jb < ncol; jb += 32) {
+        const int j = k + 1 + jb + lane;
+        if (j < LD) {
+          const double u = A[k * LD + j];
+          for (int i = k + 1; i < N; ++i) A[i * LD + j] = fma(-mult[i], u, A[i * LD + j]);
+        }
+      }
+      __syncwarp();
+    }
+    if (singular) {
+      if (lane == 0) {
+        a.z[t] = qnan;
+        a.sigma[t] = qnan;
+        a.status[t] = SKG_KRIGE_SINGULAR;
+      }
+      __syncwarp();
+      continue;
+    }
+    // back substitution; solution overwrites the rhs column A[i*LD + N]
+    for (int i = N - 1; i >= 0; --i) {
+      double acc = 0.0;
+      for (int j = i + 1 + lane; j < N; j += 32) acc = fma(A[i * LD + j], A[j * LD + N], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) A[i * LD + N] = (A[i * LD + N] - acc) / A[i * LD + i];
+      __syncwarp();
+    }
+    double sz = 0.0, ss = 0.0;
+    for (int i = lane; i < nn; i += 32) {
+      const double w = A[i * LD + N];
+      sz = fma(w, nval[i], sz);   // Kriging.py:647
+      ss = fma(w, rhs[i], ss);    // Kriging.py:644
+    }
+    sz = warp_sum(sz);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      a.z[t] = sz;
+      a.sigma[t] = ss + A[nn * LD + N];
+      a.status[t] = SKG_KRIGE_OK;
+    }
+    __syncwarp();
+  }
+}
+
+static int parse_grid(const double* grid, int dim, GridParams* g) {
+  if (!grid) { set_error("grid NULL"); return SKG_E_BADARG; }
+  g->ox = grid[0]; g->oy = grid[1]; g->oz = grid[2]; g->h = grid[3];
+  g->nx = (int)grid[4]; g->ny = (int)grid[5]; g->nz = dim == 3 ? (int)grid[6] : 1;
+  if (!(g->h > 0.0) || g->nx < 1 || g->ny < 1 || g->nz < 1 ||
+      (double)g->nx * g->ny * g->nz > 2.0e9) {
+    set_error("bad grid: h=%g nx=%d ny=%d nz=%d", g->h, g->nx, g->ny, g->nz);
+    return SKG_E_BADARG;
+  }
+  return 0;
+}
+
+static void krige_layout(int max_points, int dim, int* cap, int* region, int* per_warp) {
+  const int N = max_points + 1;
+  int reg = N * ((N + 1) | 1) * 8;
+  reg = std::max(reg, 1024 * 12);
+  reg = (reg + 15) & ~15;
+  *cap = reg / 12;
+  *region = reg;
+  *per_warp = reg + (dim + 1) * max_points * 8 + 2 * (max_points + 1) * 8;
+}
+
+}  // namespace skg
+
+using namespace skg;
+
+extern "C" {
+
+int skg_krige_build_grid(const double* coords, int64_t n, int dim, const double* grid,
+                         int32_t* cell_start, int32_t* order, void* scratch,
+                         int64_t scratch_bytes, void* stream) {
+  if (!coords || n < 1 || !cell_start || !order) { set_error("NULL argument or n < 1"); return SKG_E_BADARG; }
+  if (dim != 2 && dim != 3) { set_error("dim=%d unsupported", dim); return SKG_E_UNSUPPORTED; }
+  if (n > 2000000000ll) { set_error("n too large"); return SKG_E_UNSUPPORTED; }
+  GridParams g;
+  int rc = parse_grid(grid, dim, &g);
+  if (rc) return rc;
+  const int64_t ncell = (int64_t)g.nx * g.ny * g.nz;
+  if (!scratch || scratch_bytes < (ncell + n) * 4) {
+    set_error("scratch too small: need %lld bytes", (long long)((ncell + n) * 4));
+    return SKG_E_SCRATCH;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int* counts = reinterpret_cast<int*>(scratch);
+  int* cellid = counts + ncell;
+  SKG_CUDA(cudaMemsetAsync(counts, 0, ncell * 4, st));
+  const int threads = 256;
+  const unsigned nblk = (unsigned)((n + threads - 1) / threads);
+  if (dim == 3) grid_count_kernel<3><<<nblk, threads, 0, st>>>(coords, n, g, cellid, counts);
+  else grid_count_kernel<2><<<nblk, threads, 0, st>>>(coords, n, g, cellid, counts);
+  grid_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)ncell, cell_start);
+  grid_scatter_kernel<<<nblk, threads, 0, st>>>(cellid, n, counts, order);
+  grid_sort_cells_kernel<<<(unsigned)((ncell + threads - 1) / threads), threads, 0, st>>>(
+      cell_start, (int)ncell, order);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t skg_krige_scratch_bytes(int max_points) {
+  (void)max_points;
+  return 16;  // the warp-per-target kernel keeps everything in shared memory
+}
+
+int skg_krige(const double* coords, const double* values, int64_t n, int dim, const double* grid,
+              const int32_t* cell_start, const int32_t* order, const double* targets, int64_t m,
+              int model, const double* model_params, double radius, int min_points, int max_points,
+              double* z, double* sigma, int32_t* status, void* scratch, int64_t scratch_bytes,
+              int64_t target_begin, int64_t target_end, void* stream) {
+  (void)scratch; (void)scratch_bytes;
+  if (!coords || !values || !cell_start || !order || !targets || !model_params || !z || !sigma || !status) {
+    set_error("NULL argument");
+    return SKG_E_BADARG;
+  }
+  if (dim != 2 && dim != 3) { set_error("dim=%d unsupported", dim); return SKG_E_UNSUPPORTED; }
+  if (n < 1 || m < 0 || target_begin < 0 || target_end < target_begin || target_end > m) {
+    set_error("bad sizes / target range");
+    return SKG_E_BADARG;
+  }
+  if (max_points < 1 || max_points > SKG_KRIGE_MAX_POINTS) {
+    set_error("max_points=%d outside [1, %d]", max_points, SKG_KRIGE_MAX_POINTS);
+    return SKG_E_UNSUPPORTED;
+  }
+  if (min_points < 0 || min_points > max_points) { set_error("min_points outside [0, max_points]"); return SKG_E_BADARG; }
+  if (model < SKG_MODEL_SPHERICAL || model > SKG_MODEL_STABLE) { set_error("unknown model id %d", model); return SKG_E_BADARG; }
+  if (!(radius >= 0.0)) { set_error("radius must be >= 0"); return SKG_E_BADARG; }
+  KrigeArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int rc = parse_grid(grid, dim, &a.grid);
+  if (rc) return rc;
+  a.coords = coords; a.values = values; a.n = n;
+  a.cell_start = cell_start; a.order = order; a.targets = targets; a.m = m;
+  a.model.model = model;
+  a.model.r = model_params[0]; a.model.c0 = model_params[1];
+  a.model.s = model_params[2]; a.model.b = model_params[3];
+  switch (model) {
+    case SKG_MODEL_SPHERICAL: a.model.a = a.model.r / 1.0; break;
+    case SKG_MODEL_EXPONENTIAL: a.model.a = a.model.r / 3.0; break;
+    case SKG_MODEL_GAUSSIAN: a.model.a = a.model.r / 2.0; break;
+    case SKG_MODEL_CUBIC: a.model.a = a.model.r / 1.0; break;
+    default: a.model.a = a.model.r / std::pow(3.0, 1.0 / a.model.s); break;
+  }
+  a.radius = radius; a.min_points = min_points; a.max_points = max_points;
+  a.z = z; a.sigma = sigma; a.status = status; a.t0 = target_begin; a.t1 = target_end;
+  if (target_end == target_begin) return 0;
+  int per_warp = 0;
+  krige_layout(max_points, dim, &a.cap, &a.region_bytes, &per_warp);
+  const int smem_max = 220 * 1024;
+  int wpb = std::min(8, smem_max / per_warp);
+  if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
+  const size_t smem = (size_t)wpb * per_warp;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto kern = dim == 3 ? krige_kernel<3> : krige_kernel<2>;
+  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+  occ = std::max(1, occ);
+  const int64_t ntarget = target_end - target_begin;
+  const int64_t grid_blocks = std::min<int64_t>((ntarget + wpb - 1) / wpb, (int64_t)sm_count() * occ);
+  kern<<<(unsigned)grid_blocks, wpb * 32, smem, st>>>(a);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

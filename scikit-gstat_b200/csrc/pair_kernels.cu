@@ -1,0 +1,763 @@
+// Pair-sweep kernels (K1-K4 of SURVEY.md section 2.2) for sm_100a.
+//
+// All kernels walk the upper triangle of the N x N pair matrix in
+// TILE x TILE point tiles.  A CTA of BLOCK threads keeps RI = TILE/BLOCK
+// "i" points per thread in registers, stages the "j" tile in shared memory with
+// coalesced loads and reads it back as warp-wide broadcasts.  The N(N-1)/2
+// distance vector the reference materialises (MetricSpace.py:151-153,
+// Variogram.py:1202-1208) never exists.
+//
+// Per pair:  s = fl(fl(dx*dx) + fl(dy*dy)) [+ fl(dw*dw)]  - scipy's euclidean
+// operand order, no FMA (explicit __dmul_rn/__dadd_rn), so that every
+// comparison against the squared-space thresholds reproduces np.digitize on
+// d = sqrt(s) exactly (see include/skg_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace skg {
+
+// ------------------------------------------------------------------ sweep ---
+
+template <int DIM>
+struct TileSmem {
+  double x[TILE];
+  double y[TILE];
+  double w[DIM == 3 ? TILE : 1];
+  double z[TILE];
+};
+
+// Generic sweep over tiles [t0, t1) with static striding over the grid.
+// Op must provide: void pair(double s, double dx, double dy, double zi, double zj, int64_t gi, int64_t gj)
+template <int DIM, class Op>
+__device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
+                                            const double* __restrict__ values, int64_t n,
+                                            int64_t t0, int64_t t1, TileSmem<DIM>& sm, Op& op) {
+  const int tid = threadIdx.x;
+  const int64_t nt = (n + TILE - 1) / TILE;
+  const double qnan = __longlong_as_double(NAN_BITS);
+  const double* __restrict__ X = coords;
+  const double* __restrict__ Y = coords + n;
+  const double* __restrict__ W = coords + 2 * n;
+
+  for (int64_t t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+    int I, J;
+    tile_decode(t, nt, I, J);
+    double xi[RI], yi[RI], wi[RI], zi[RI];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      int64_t i = (int64_t)I * TILE + r * BLOCK + tid;
+      bool v = i < n;
+      xi[r] = v ? X[i] : qnan;
+      yi[r] = v ? Y[i] : qnan;
+      wi[r] = (DIM == 3 && v) ? W[i] : (DIM == 3 ? qnan : 0.0);
+      zi[r] = (v && values) ? values[i] : 0.0;
+    }
+    __syncthreads();  // all reads of the previous j tile are done
+    for (int k = tid; k < TILE; k += BLOCK) {
+      int64_t j = (int64_t)J * TILE + k;
+      bool v = j < n;
+      sm.x[k] = v ? X[j] : qnan;
+      sm.y[k] = v ? Y[j] : qnan;
+      if (DIM == 3) sm.w[k] = v ? W[j] : qnan;
+      sm.z[k] = (v && values) ? values[j] : 0.0;
+    }
+    __syncthreads();
+    const bool diag = (I == J);
+    int64_t jn = n - (int64_t)J * TILE;
+    const int jcount = jn < TILE ? (int)jn : TILE;
+#pragma unroll 2
+    for (int jj = 0; jj < jcount; ++jj) {
+      const double xj = sm.x[jj], yj = sm.y[jj], zj = sm.z[jj];
+      const double wj = (DIM == 3) ? sm.w[jj] : 0.0;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        double dx = xi[r] - xj;
+        double dy = yi[r] - yj;
+        double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (DIM == 3) {
+          double dw = wi[r] - wj;
+          s = __dadd_rn(s, __dmul_rn(dw, dw));
+        }
+        if (diag && jj <= r * BLOCK + tid) s = qnan;  // keep i < j only
+        op.pair(s, dx, dy, zi[r], zj, (int64_t)I * TILE + r * BLOCK + tid, (int64_t)J * TILE + jj);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load_tables(const BinTable& tab, uint64_t* sThr, uint8_t* sLut) {
+  for (int k = threadIdx.x; k < THR_MAX; k += blockDim.x) sThr[k] = tab.thr[k];
+  for (int k = threadIdx.x; k < tab.ncell; k += blockDim.x) sLut[k] = tab.lut[k];
+}
+
+// -------------------------------------------------------------- K2: hist ---
+
+struct HistPartial {  // one per (CTA, lag class)
+  unsigned long long count;
+  double sum_sq;
+  double sum_sqrt;
+};
+
+template <bool DIR, int STATS, bool PRIV>
+struct HistOp {
+  const uint64_t* sThr;
+  const uint8_t* sLut;
+  int key0, shift, ncell, emax, nb;
+  unsigned* cnt;  // PRIV: already offset by tid, stride BLOCK per class
+  double* sq;
+  double* rt;
+  const DirParams* dp;
+  __device__ __forceinline__ void pair(double s, double dx, double dy, double zi, double zj, int64_t, int64_t) {
+    const uint64_t sb = (uint64_t)__double_as_longlong(s);
+    const int g = find_bin(sb, sThr, sLut, key0, shift, ncell, emax);
+    if (g < nb) {
+      if (DIR) {
+        if (!dir_mask(dx, dy, s, *dp)) return;
+      }
+      const double dz = zi - zj;
+      if (PRIV) {
+        const int a = g * BLOCK;
+        cnt[a] += 1u;
+        if (STATS & SKG_STAT_SUM_SQ) sq[a] = fma(dz, dz, sq[a]);
+        if (STATS & SKG_STAT_SUM_SQRT) rt[a] += sqrt(fabs(dz));
+      } else {
+        atomicAdd(&cnt[g], 1u);
+        if (STATS & SKG_STAT_SUM_SQ) atomicAdd(&sq[g], dz * dz);
+        if (STATS & SKG_STAT_SUM_SQRT) atomicAdd(&rt[g], sqrt(fabs(dz)));
+      }
+    }
+  }
+};
+
+// smem layout (dynamic): TileSmem | thr[THR_MAX] u64 | sq[nb*S] | rt[nb*S] | cnt[nb*S] | lut
+// with S = BLOCK (private per-thread accumulators) or 1 (shared + atomics).
+template <int DIM, bool DIR, int STATS, bool PRIV>
+__global__ void __launch_bounds__(BLOCK)
+pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
+                 const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
+                 HistPartial* __restrict__ partial, int64_t t0, int64_t t1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<DIM>& sm = *reinterpret_cast<TileSmem<DIM>*>(smem_raw);
+  uint64_t* sThr = reinterpret_cast<uint64_t*>(smem_raw + sizeof(TileSmem<DIM>));
+  const int nb = tab.nb;
+  const int S = PRIV ? BLOCK : 1;
+  double* sSq = reinterpret_cast<double*>(sThr + THR_MAX);
+  double* sRt = sSq + ((STATS & SKG_STAT_SUM_SQ) ? nb * S : 0);
+  unsigned* sCnt = reinterpret_cast<unsigned*>(sRt + ((STATS & SKG_STAT_SUM_SQRT) ? nb * S : 0));
+  uint8_t* sLut = reinterpret_cast<uint8_t*>(sCnt + nb * S);
+  const int tid = threadIdx.x;
+
+  load_tables(tab, sThr, sLut);
+  for (int k = tid; k < nb * S; k += BLOCK) {
+    sCnt[k] = 0u;
+    if (STATS & SKG_STAT_SUM_SQ) sSq[k] = 0.0;
+    if (STATS & SKG_STAT_SUM_SQRT) sRt[k] = 0.0;
+  }
+  __syncthreads();
+
+  HistOp<DIR, STATS, PRIV> op;
+  op.sThr = sThr; op.sLut = sLut;
+  op.key0 = tab.key0; op.shift = tab.shift; op.ncell = tab.ncell; op.emax = tab.emax; op.nb = nb;
+  op.cnt = sCnt + (PRIV ? tid : 0);
+  op.sq = sSq + (PRIV ? tid : 0);
+  op.rt = sRt + (PRIV ? tid : 0);
+  op.dp = &dp;
+  sweep_tiles<DIM>(coords, values, n, t0, t1, sm, op);
+  __syncthreads();
+
+  // fixed-order block reduction of the per-thread accumulators
+  HistPartial* out = partial + (int64_t)blockIdx.x * nb;
+  if (PRIV) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int g = warp; g < nb; g += BLOCK / 32) {
+      unsigned long long c = 0;
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int k = 0; k < BLOCK / 32; ++k) {
+        const int idx = g * BLOCK + lane + 32 * k;
+        c += sCnt[idx];
+        if (STATS & SKG_STAT_SUM_SQ) a += sSq[idx];
+        if (STATS & SKG_STAT_SUM_SQRT) b += sRt[idx];
+      }
+      c = warp_sum(c);
+      if (STATS & SKG_STAT_SUM_SQ) a = warp_sum(a);
+      if (STATS & SKG_STAT_SUM_SQRT) b = warp_sum(b);
+      if (lane == 0) {
+        out[g].count = c;
+        out[g].sum_sq = a;
+        out[g].sum_sqrt = b;
+      }
+    }
+  } else {
+    for (int g = tid; g < nb; g += BLOCK) {
+      out[g].count = sCnt[g];
+      out[g].sum_sq = (STATS & SKG_STAT_SUM_SQ) ? sSq[g] : 0.0;
+      out[g].sum_sqrt = (STATS & SKG_STAT_SUM_SQRT) ? sRt[g] : 0.0;
+    }
+  }
+}
+
+__global__ void pair_hist_reduce_kernel(const HistPartial* __restrict__ partial, int nblocks, int nb,
+                                        unsigned long long* __restrict__ count,
+                                        double* __restrict__ sum_sq, double* __restrict__ sum_sqrt) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nb) return;
+  unsigned long long c = 0;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nblocks; ++k) {
+    const HistPartial p = partial[(int64_t)k * nb + g];
+    c += p.count;
+    a += p.sum_sq;
+    b += p.sum_sqrt;
+  }
+  count[g] += c;
+  if (sum_sq) sum_sq[g] += a;
+  if (sum_sqrt) sum_sqrt[g] += b;
+}
+
+// ------------------------------------------------- K1/K3: select passes ---
+
+template <bool DIR, bool SEG, int KEY, bool GATHER>
+struct SelectOp {
+  const uint64_t* sThr;
+  const uint8_t* sLut;
+  int key0, shift, ncell, emax, nb;
+  const DirParams* dp;
+  const SegTable* seg;
+  long long nbuckets;
+  unsigned long long* hist;
+  unsigned long long local_max;
+  // gather
+  const uint32_t* bitmap;
+  double* cand_key;
+  uint32_t* cand_slot;
+  unsigned long long* cand_count;
+  long long capacity;
+
+  __device__ __forceinline__ void pair(double s, double dx, double dy, double zi, double zj, int64_t, int64_t) {
+    const uint64_t sb = (uint64_t)__double_as_longlong(s);
+    if (sb > INF_BITS) return;  // NaN: padded / i>=j / NaN coordinate
+    int g = 0;
+    if (SEG) {
+      g = find_bin(sb, sThr, sLut, key0, shift, ncell, emax);
+      if (g >= nb) return;
+    }
+    if (DIR) {
+      if (!dir_mask(dx, dy, s, *dp)) return;
+    }
+    const double key = (KEY == SKG_KEY_SQDIST) ? s : fabs(zi - zj);
+    const uint64_t kb = (uint64_t)__double_as_longlong(key);
+    if (kb > INF_BITS) return;
+    if (!SEG && !GATHER) local_max = kb > local_max ? kb : local_max;
+    if (kb < seg->lo_bits[g] || kb >= seg->hi_bits[g]) return;
+    const double lo = __longlong_as_double((long long)seg->lo_bits[g]);
+    long long b = __double2ll_rz(__dmul_rn(__dsub_rn(key, lo), seg->scale[g]));
+    b = b < nbuckets - 1 ? b : nbuckets - 1;
+    const long long slot = (long long)g * nbuckets + b;
+    if (!GATHER) {
+      atomicAdd(&hist[slot], 1ull);
+    } else {
+      if ((bitmap[slot >> 5] >> (slot & 31)) & 1u) {
+        const unsigned long long pos = atomicAdd(cand_count, 1ull);
+        if ((long long)pos < capacity) {
+          cand_key[pos] = key;
+          cand_slot[pos] = (uint32_t)slot;
+        }
+      }
+    }
+  }
+};
+
+template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER>
+__global__ void __launch_bounds__(BLOCK)
+pair_select_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
+                   const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
+                   const __grid_constant__ SegTable seg_tab, long long nbuckets,
+                   unsigned long long* __restrict__ hist, unsigned long long* __restrict__ max_bits,
+                   const uint32_t* __restrict__ bitmap, double* __restrict__ cand_key,
+                   uint32_t* __restrict__ cand_slot, unsigned long long* __restrict__ cand_count,
+                   long long capacity, int64_t t0, int64_t t1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<DIM>& sm = *reinterpret_cast<TileSmem<DIM>*>(smem_raw);
+  uint64_t* sThr = reinterpret_cast<uint64_t*>(smem_raw + sizeof(TileSmem<DIM>));
+  SegTable* sSeg = reinterpret_cast<SegTable*>(sThr + THR_MAX);
+  uint8_t* sLut = reinterpret_cast<uint8_t*>(sSeg + 1);
+  load_tables(tab, sThr, sLut);
+  const int nseg = SEG ? tab.nb : 1;
+  for (int k = threadIdx.x; k < nseg; k += BLOCK) {
+    sSeg->lo_bits[k] = seg_tab.lo_bits[k];
+    sSeg->hi_bits[k] = seg_tab.hi_bits[k];
+    sSeg->scale[k] = seg_tab.scale[k];
+  }
+  __syncthreads();
+  SelectOp<DIR, SEG, KEY, GATHER> op;
+  op.sThr = sThr; op.sLut = sLut;
+  op.key0 = tab.key0; op.shift = tab.shift; op.ncell = tab.ncell; op.emax = tab.emax; op.nb = tab.nb;
+  op.dp = &dp; op.seg = sSeg; op.nbuckets = nbuckets; op.hist = hist; op.local_max = 0ull;
+  op.bitmap = bitmap; op.cand_key = cand_key; op.cand_slot = cand_slot;
+  op.cand_count = cand_count; op.capacity = capacity;
+  sweep_tiles<DIM>(coords, values, n, t0, t1, sm, op);
+  if (!SEG && !GATHER && max_bits) {
+    unsigned long long m = op.local_max;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_down_sync(0xffffffffu, m, o);
+      m = other > m ? other : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_bits, m);
+  }
+}
+
+// ------------------------------------------- guard-band pair collection ---
+
+struct AmbOp {
+  const DirParams* dp;
+  int* out_i;
+  int* out_j;
+  unsigned long long* count;
+  long long capacity;
+  __device__ __forceinline__ void pair(double s, double dx, double dy, double, double, int64_t gi, int64_t gj) {
+    if (!(s > 0.0)) return;
+    bool amb;
+    dir_fast(dx, dy, *dp, &amb);
+    if (amb) {
+      const unsigned long long pos = atomicAdd(count, 1ull);
+      if ((long long)pos < capacity) {
+        out_i[pos] = (int)gi;
+        out_j[pos] = (int)gj;
+      }
+    }
+  }
+};
+
+__global__ void __launch_bounds__(BLOCK)
+pair_dir_ambiguous_kernel(const double* __restrict__ coords, int64_t n,
+                          const __grid_constant__ DirParams dp, int* __restrict__ out_i,
+                          int* __restrict__ out_j, unsigned long long* __restrict__ count,
+                          long long capacity, int64_t t0, int64_t t1) {
+  __shared__ TileSmem<2> sm;
+  AmbOp op;
+  op.dp = &dp; op.out_i = out_i; op.out_j = out_j; op.count = count; op.capacity = capacity;
+  sweep_tiles<2>(coords, nullptr, n, t0, t1, sm, op);
+}
+
+// ------------------------------------------------------- materialisation ---
+
+template <int DIM>
+__global__ void pair_materialize_kernel(const double* __restrict__ coords,
+                                        const double* __restrict__ values, int64_t n,
+                                        const __grid_constant__ BinTable tab,
+                                        const __grid_constant__ DirParams dp, int use_dir,
+                                        double* __restrict__ dist, double* __restrict__ diffs,
+                                        long long* __restrict__ groups, uint8_t* __restrict__ mask,
+                                        int64_t k0, int64_t k1) {
+  const double* X = coords;
+  const double* Y = coords + n;
+  const double* W = coords + 2 * n;
+  for (int64_t k = k0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < k1;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    // condensed index -> (i, j): rowstart(i) = i*n - i(i+1)/2
+    double nn = (double)n;
+    int64_t i = (int64_t)(nn - 0.5 - sqrt((nn - 0.5) * (nn - 0.5) - 2.0 * (double)k));
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    while (i > 0 && i * n - i * (i + 1) / 2 > k) --i;
+    while ((i + 1) * n - (i + 1) * (i + 2) / 2 <= k) ++i;
+    const int64_t j = k - (i * n - i * (i + 1) / 2) + i + 1;
+    const double dx = X[i] - X[j];
+    const double dy = Y[i] - Y[j];
+    double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (DIM == 3) {
+      const double dw = W[i] - W[j];
+      s = __dadd_rn(s, __dmul_rn(dw, dw));
+    }
+    const int64_t o = k - k0;
+    bool m = true;
+    if (use_dir) m = dir_mask(dx, dy, s, dp);
+    if (dist) dist[o] = sqrt(s);
+    if (diffs) diffs[o] = fabs(values[i] - values[j]);
+    if (mask) mask[o] = m ? 1 : 0;
+    if (groups) {
+      const uint64_t sb = (uint64_t)__double_as_longlong(s);
+      int g = 0;
+      for (int e = 0; e < tab.nb; ++e) g += (sb >= tab.thr[e]) ? 1 : 0;
+      groups[o] = (g >= tab.nb || !m) ? -1 : g;
+    }
+  }
+}
+
+// ------------------------------------------------------------ host side ---
+
+// T(e) thresholds arrive as bit patterns.  cell(x) = (hi32(x) >> shift) - key0,
+// clamped to [0, ncell-1]; lut[c] = number of thresholds in strictly lower
+// cells; emax = max number of thresholds sharing one cell.
+int build_bin_table(const uint64_t* thr_bits, int n_lags, BinTable* out) {
+  std::memset(out, 0, sizeof(BinTable));
+  for (int k = 0; k < THR_MAX; ++k) out->thr[k] = ~0ull;
+  out->nb = n_lags;
+  out->shift = 0; out->key0 = 0; out->ncell = 1; out->emax = 0;
+  out->lut[0] = 0;
+  if (n_lags == 0) return 0;
+  if (n_lags < 0 || n_lags > SKG_MAX_LAGS) {
+    set_error("n_lags=%d outside [0, %d]", n_lags, SKG_MAX_LAGS);
+    return SKG_E_BADARG;
+  }
+  for (int k = 0; k < n_lags; ++k) {
+    if (k && thr_bits[k] < thr_bits[k - 1]) {
+      set_error("lag thresholds must be non-decreasing (k=%d)", k);
+      return SKG_E_BADARG;
+    }
+    if (thr_bits[k] > INF_BITS) {
+      set_error("lag threshold %d is NaN", k);
+      return SKG_E_BADARG;
+    }
+    out->thr[k] = thr_bits[k];
+  }
+  const uint32_t hi_last = (uint32_t)(thr_bits[n_lags - 1] >> 32);
+  // lowest key worth resolving: at most 48 octaves below the last threshold
+  uint32_t hi_first = (uint32_t)(thr_bits[0] >> 32);
+  const uint32_t floor_hi = hi_last > (48u << 20) ? hi_last - (48u << 20) : 0u;
+  if (hi_first < floor_hi) hi_first = floor_hi;
+  int shift = 0;
+  for (; shift < 31; ++shift) {
+    int64_t cells = (int64_t)(hi_last >> shift) - (int64_t)(hi_first >> shift) + 3;
+    if (cells <= LUT_MAX) break;
+  }
+  const int key0 = (int)(hi_first >> shift) - 1;  // cell 0: everything below the first threshold's cell
+  const int ncell = (int)(hi_last >> shift) - key0 + 2;  // top cell: above the last threshold's cell
+  out->shift = shift; out->key0 = key0; out->ncell = ncell;
+  int per_cell[LUT_MAX];
+  std::memset(per_cell, 0, sizeof(per_cell));
+  for (int k = 0; k < n_lags; ++k) {
+    int c = (int)((uint32_t)(thr_bits[k] >> 32) >> shift) - key0;
+    c = std::min(std::max(c, 0), ncell - 1);
+    per_cell[c]++;
+  }
+  int run = 0, emax = 0;
+  for (int c = 0; c < ncell; ++c) {
+    out->lut[c] = (uint8_t)run;
+    run += per_cell[c];
+    emax = std::max(emax, per_cell[c]);
+  }
+  out->emax = emax;
+  return 0;
+}
+
+int build_dir_params(const double* dir, int dim, DirParams* out) {
+  std::memset(out, 0, sizeof(DirParams));
+  if (!dir) return 0;
+  const int model = (int)dir[0];
+  if (model == SKG_DIR_NONE) return 0;
+  if (model != SKG_DIR_TRIANGLE && model != SKG_DIR_COMPASS) {
+    set_error("unknown directional model id %d", model);
+    return SKG_E_BADARG;
+  }
+  if (dim != 2) {
+    set_error("directional mask needs 2-D coordinates (DirectionalVariogram.py:359-364)");
+    return SKG_E_UNSUPPORTED;
+  }
+  out->model = model;
+  out->az_rad = dir[1];
+  out->half_tol_rad = dir[2];
+  out->half_bw = dir[3];
+  out->cos_az = std::cos(dir[1]);
+  out->sin_az = std::sin(dir[1]);
+  const double half_pi = 3.141592653589793 / 2;
+  out->tol_all = dir[2] >= half_pi ? 1 : 0;
+  out->tan_ht = out->tol_all ? 0.0 : std::tan(dir[2]);
+  out->amb_exclude = dir[4] != 0.0 ? 1 : 0;
+  return 0;
+}
+
+static int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0, int64_t t1) {
+  if (!coords || n < 0) { set_error("coords NULL or n < 0"); return SKG_E_BADARG; }
+  if (dim != 2 && dim != 3) {
+    set_error("dim=%d unsupported (2 or 3; pad 1-D input with a zero column)", dim);
+    return SKG_E_UNSUPPORTED;
+  }
+  const int64_t ntiles = skg_pair_num_tiles(n);
+  if (t0 < 0 || t1 < t0 || t1 > ntiles) {
+    set_error("tile range [%lld, %lld) outside [0, %lld]", (long long)t0, (long long)t1,
+              (long long)ntiles);
+    return SKG_E_BADARG;
+  }
+  return 0;
+}
+
+constexpr int MAX_GRID_PER_SM = 8;
+
+static size_t hist_smem_bytes(int dim, int nb, int stats, bool priv) {
+  const size_t S = priv ? BLOCK : 1;
+  size_t b = (dim == 3 ? sizeof(TileSmem<3>) : sizeof(TileSmem<2>)) + THR_MAX * 8;
+  if (stats & SKG_STAT_SUM_SQ) b += (size_t)nb * S * 8;
+  if (stats & SKG_STAT_SUM_SQRT) b += (size_t)nb * S * 8;
+  b += (size_t)nb * S * 4;
+  b += LUT_MAX;
+  return b;
+}
+
+template <int DIM, bool DIR, int STATS, bool PRIV>
+static int launch_hist(const double* coords, const double* values, int64_t n, const BinTable& tab,
+                       const DirParams& dp, HistPartial* partial, int max_blocks, int64_t t0,
+                       int64_t t1, size_t smem, cudaStream_t st, int* nblocks_out) {
+  auto kern = pair_hist_kernel<DIM, DIR, STATS, PRIV>;
+  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+  if (occ < 1) { set_error("pair_hist kernel does not fit (smem=%zu)", smem); return SKG_E_UNSUPPORTED; }
+  occ = std::min(occ, MAX_GRID_PER_SM);
+  int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, t1 - t0);
+  grid = std::min<int64_t>(grid, max_blocks);
+  *nblocks_out = (int)grid;
+  kern<<<(unsigned)grid, BLOCK, smem, st>>>(coords, values, n, tab, dp, partial, t0, t1);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int DIM, bool DIR, bool PRIV>
+static int dispatch_hist_stats(int stats, const double* coords, const double* values, int64_t n,
+                               const BinTable& tab, const DirParams& dp, HistPartial* partial,
+                               int max_blocks, int64_t t0, int64_t t1, size_t smem,
+                               cudaStream_t st, int* nb_out) {
+  switch (stats) {
+    case 0: return launch_hist<DIM, DIR, 0, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+    case 1: return launch_hist<DIM, DIR, 1, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+    case 2: return launch_hist<DIM, DIR, 2, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+    default: return launch_hist<DIM, DIR, 3, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+  }
+}
+
+template <bool PRIV>
+static int dispatch_hist(int dim, bool dir, int stats, const double* coords, const double* values,
+                         int64_t n, const BinTable& tab, const DirParams& dp, HistPartial* partial,
+                         int max_blocks, int64_t t0, int64_t t1, size_t smem, cudaStream_t st,
+                         int* nb_out) {
+  if (dim == 3) return dispatch_hist_stats<3, false, PRIV>(stats, coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+  if (dir) return dispatch_hist_stats<2, true, PRIV>(stats, coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+  return dispatch_hist_stats<2, false, PRIV>(stats, coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+}
+
+template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER>
+static int launch_select(const double* coords, const double* values, int64_t n, const BinTable& tab,
+                         const DirParams& dp, const SegTable& seg_tab, int64_t nbuckets,
+                         uint64_t* hist, uint64_t* max_bits, const uint32_t* bitmap,
+                         double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
+                         int64_t capacity, int64_t t0, int64_t t1, cudaStream_t st) {
+  auto kern = pair_select_kernel<DIM, DIR, SEG, KEY, GATHER>;
+  const size_t smem = sizeof(TileSmem<DIM>) + THR_MAX * 8 + sizeof(SegTable) + LUT_MAX;
+  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+  occ = std::max(1, std::min(occ, MAX_GRID_PER_SM));
+  const int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, t1 - t0);
+  kern<<<(unsigned)grid, BLOCK, smem, st>>>(
+      coords, values, n, tab, dp, seg_tab, (long long)nbuckets,
+      reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(max_bits),
+      bitmap, cand_key, cand_slot, reinterpret_cast<unsigned long long*>(cand_count),
+      (long long)capacity, t0, t1);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <bool GATHER, typename... A>
+static int dispatch_select(int dim, bool dir, bool seg, int key, const A&... a) {
+#define SKG_SEL(D, DR, SG, K) return launch_select<D, DR, SG, K, GATHER>(a...)
+  if (dim == 3) {
+    if (seg) { if (key == SKG_KEY_SQDIST) SKG_SEL(3, false, true, 0); else SKG_SEL(3, false, true, 1); }
+    else     { if (key == SKG_KEY_SQDIST) SKG_SEL(3, false, false, 0); else SKG_SEL(3, false, false, 1); }
+  }
+  if (dir) {
+    if (seg) { if (key == SKG_KEY_SQDIST) SKG_SEL(2, true, true, 0); else SKG_SEL(2, true, true, 1); }
+    else     { if (key == SKG_KEY_SQDIST) SKG_SEL(2, true, false, 0); else SKG_SEL(2, true, false, 1); }
+  }
+  if (seg) { if (key == SKG_KEY_SQDIST) SKG_SEL(2, false, true, 0); else SKG_SEL(2, false, true, 1); }
+  if (key == SKG_KEY_SQDIST) SKG_SEL(2, false, false, 0);
+  SKG_SEL(2, false, false, 1);
+#undef SKG_SEL
+}
+
+static int select_common(bool gather, const double* coords, const double* values, int64_t n,
+                         int dim, const double* dir, const uint64_t* thr_bits, int n_lags,
+                         int key_kind, const uint64_t* seg_lo_bits, const uint64_t* seg_hi_bits,
+                         const double* seg_scale, int64_t n_buckets, uint64_t* hist,
+                         uint64_t* max_bits, const uint32_t* bitmap, double* cand_key,
+                         uint32_t* cand_slot, uint64_t* cand_count, int64_t capacity,
+                         int64_t t0, int64_t t1, void* stream) {
+  int rc = check_pair_args(coords, n, dim, t0, t1);
+  if (rc) return rc;
+  if (key_kind != SKG_KEY_SQDIST && key_kind != SKG_KEY_ABSDZ) { set_error("bad key_kind"); return SKG_E_BADARG; }
+  if (key_kind == SKG_KEY_ABSDZ && !values) { set_error("values required for |dz| keys"); return SKG_E_BADARG; }
+  if (n_buckets < 1 || !seg_lo_bits || !seg_hi_bits || !seg_scale) { set_error("bad segment window arguments"); return SKG_E_BADARG; }
+  if (n_lags > 0 && !thr_bits) { set_error("thr_bits NULL"); return SKG_E_BADARG; }
+  const int nseg = n_lags > 0 ? n_lags : 1;
+  if ((double)nseg * (double)n_buckets >= 4294967296.0) { set_error("nseg*n_buckets must fit 32 bits"); return SKG_E_BADARG; }
+  BinTable tab;
+  rc = build_bin_table(thr_bits, n_lags > 0 ? n_lags : 0, &tab);
+  if (rc) return rc;
+  DirParams dp;
+  rc = build_dir_params(dir, dim, &dp);
+  if (rc) return rc;
+  if (t1 == t0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SegTable host_seg;
+  std::memset(&host_seg, 0, sizeof(host_seg));
+  for (int k = 0; k < nseg; ++k) {
+    host_seg.lo_bits[k] = seg_lo_bits[k];
+    host_seg.hi_bits[k] = seg_hi_bits[k];
+    host_seg.scale[k] = seg_scale[k];
+  }
+  if (gather)
+    rc = dispatch_select<true>(dim, dp.model != SKG_DIR_NONE, n_lags > 0, key_kind, coords, values, n,
+                               tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
+                               cand_key, cand_slot, cand_count, capacity, t0, t1, st);
+  else
+    rc = dispatch_select<false>(dim, dp.model != SKG_DIR_NONE, n_lags > 0, key_kind, coords, values, n,
+                                tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
+                                cand_key, cand_slot, cand_count, capacity, t0, t1, st);
+  return rc;
+}
+
+}  // namespace skg
+
+using namespace skg;
+
+extern "C" {
+
+int64_t skg_pair_num_tiles(int64_t n) {
+  if (n <= 1) return 0;
+  const int64_t nt = (n + TILE - 1) / TILE;
+  return nt * (nt + 1) / 2;
+}
+
+int64_t skg_pair_hist_scratch_bytes(int n_lags) {
+  if (n_lags < 1) n_lags = 1;
+  return (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
+}
+
+int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim, const double* dir,
+                  const uint64_t* thr_bits, int n_lags, int stats, uint64_t* count, double* sum_sq,
+                  double* sum_sqrt, void* scratch, int64_t scratch_bytes, int64_t tile_begin,
+                  int64_t tile_end, void* stream) {
+  int rc = check_pair_args(coords, n, dim, tile_begin, tile_end);
+  if (rc) return rc;
+  if (!values || !thr_bits || !count || n_lags < 1) { set_error("values/thr_bits/count NULL or n_lags < 1"); return SKG_E_BADARG; }
+  if ((stats & ~3) || ((stats & SKG_STAT_SUM_SQ) && !sum_sq) || ((stats & SKG_STAT_SUM_SQRT) && !sum_sqrt)) {
+    set_error("stats flags / output pointers inconsistent");
+    return SKG_E_BADARG;
+  }
+  if (!scratch || scratch_bytes < skg_pair_hist_scratch_bytes(n_lags)) {
+    set_error("scratch too small: need %lld bytes", (long long)skg_pair_hist_scratch_bytes(n_lags));
+    return SKG_E_SCRATCH;
+  }
+  BinTable tab;
+  rc = build_bin_table(thr_bits, n_lags, &tab);
+  if (rc) return rc;
+  DirParams dp;
+  rc = build_dir_params(dir, dim, &dp);
+  if (rc) return rc;
+  if (tile_end == tile_begin) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool use_dir = dp.model != SKG_DIR_NONE;
+  const int max_blocks = sm_count() * MAX_GRID_PER_SM;
+  HistPartial* partial = reinterpret_cast<HistPartial*>(scratch);
+  int nblocks = 0;
+  size_t smem = hist_smem_bytes(dim, n_lags, stats, true);
+  if (smem <= 200 * 1024) {
+    rc = dispatch_hist<true>(dim, use_dir, stats, coords, values, n, tab, dp, partial, max_blocks,
+                             tile_begin, tile_end, smem, st, &nblocks);
+  } else {
+    smem = hist_smem_bytes(dim, n_lags, stats, false);
+    rc = dispatch_hist<false>(dim, use_dir, stats, coords, values, n, tab, dp, partial, max_blocks,
+                              tile_begin, tile_end, smem, st, &nblocks);
+  }
+  if (rc) return rc;
+  pair_hist_reduce_kernel<<<(n_lags + 127) / 128, 128, 0, st>>>(
+      partial, nblocks, n_lags, reinterpret_cast<unsigned long long*>(count),
+      (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr, (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int skg_pair_select_hist(const double* coords, const double* values, int64_t n, int dim,
+                         const double* dir, const uint64_t* thr_bits, int n_lags, int key_kind,
+                         const uint64_t* seg_lo_bits, const uint64_t* seg_hi_bits,
+                         const double* seg_scale, int64_t n_buckets, uint64_t* hist,
+                         uint64_t* max_bits, int64_t tile_begin, int64_t tile_end, void* stream) {
+  if (!hist) { set_error("hist NULL"); return SKG_E_BADARG; }
+  return select_common(false, coords, values, n, dim, dir, thr_bits, n_lags, key_kind, seg_lo_bits,
+                       seg_hi_bits, seg_scale, n_buckets, hist, max_bits, nullptr, nullptr, nullptr,
+                       nullptr, 0, tile_begin, tile_end, stream);
+}
+
+int skg_pair_select_gather(const double* coords, const double* values, int64_t n, int dim,
+                           const double* dir, const uint64_t* thr_bits, int n_lags, int key_kind,
+                           const uint64_t* seg_lo_bits, const uint64_t* seg_hi_bits,
+                           const double* seg_scale, int64_t n_buckets, const uint32_t* bitmap,
+                           double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
+                           int64_t capacity, int64_t tile_begin, int64_t tile_end, void* stream) {
+  if (!bitmap || !cand_key || !cand_slot || !cand_count || capacity < 0) {
+    set_error("gather buffers NULL");
+    return SKG_E_BADARG;
+  }
+  return select_common(true, coords, values, n, dim, dir, thr_bits, n_lags, key_kind, seg_lo_bits,
+                       seg_hi_bits, seg_scale, n_buckets, nullptr, nullptr, bitmap, cand_key,
+                       cand_slot, cand_count, capacity, tile_begin, tile_end, stream);
+}
+
+int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const double* dir,
+                           int32_t* pair_i, int32_t* pair_j, uint64_t* count, int64_t capacity,
+                           int64_t tile_begin, int64_t tile_end, void* stream) {
+  int rc = check_pair_args(coords, n, dim, tile_begin, tile_end);
+  if (rc) return rc;
+  if (!dir || !pair_i || !pair_j || !count || capacity < 0) { set_error("NULL argument"); return SKG_E_BADARG; }
+  if (n > 2147483647ll) { set_error("n too large for int32 pair indices"); return SKG_E_UNSUPPORTED; }
+  DirParams dp;
+  rc = build_dir_params(dir, dim, &dp);
+  if (rc) return rc;
+  if (dp.model == SKG_DIR_NONE) { set_error("directional model required"); return SKG_E_BADARG; }
+  if (tile_end == tile_begin) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t grid = std::min<int64_t>((int64_t)sm_count() * MAX_GRID_PER_SM, tile_end - tile_begin);
+  pair_dir_ambiguous_kernel<<<(unsigned)grid, BLOCK, 0, st>>>(
+      coords, n, dp, pair_i, pair_j, reinterpret_cast<unsigned long long*>(count),
+      (long long)capacity, tile_begin, tile_end);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int skg_pair_materialize(const double* coords, const double* values, int64_t n, int dim,
+                         const double* dir, const uint64_t* thr_bits, int n_lags, double* dist,
+                         double* diffs, int64_t* groups, uint8_t* mask, int64_t pair_begin,
+                         int64_t pair_end, void* stream) {
+  if (!coords || n < 0) { set_error("coords NULL or n < 0"); return SKG_E_BADARG; }
+  if (dim != 2 && dim != 3) { set_error("dim=%d unsupported", dim); return SKG_E_UNSUPPORTED; }
+  const int64_t npairs = n * (n - 1) / 2;
+  if (pair_begin < 0 || pair_end < pair_begin || pair_end > npairs) { set_error("pair range outside [0, n(n-1)/2]"); return SKG_E_BADARG; }
+  if (diffs && !values) { set_error("values required for diffs"); return SKG_E_BADARG; }
+  if (groups && (!thr_bits || n_lags < 1)) { set_error("thr_bits required for groups"); return SKG_E_BADARG; }
+  BinTable tab;
+  int rc = build_bin_table(thr_bits, groups ? n_lags : 0, &tab);
+  if (rc) return rc;
+  DirParams dp;
+  rc = build_dir_params(dir, dim, &dp);
+  if (rc) return rc;
+  if (pair_end == pair_begin) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cnt = pair_end - pair_begin;
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>((cnt + threads - 1) / threads, (int64_t)sm_count() * 16);
+  const int use_dir = dp.model != SKG_DIR_NONE;
+  if (dim == 3)
+    pair_materialize_kernel<3><<<(unsigned)blocks, threads, 0, st>>>(
+        coords, values, n, tab, dp, use_dir, dist, diffs, (long long*)groups, mask, pair_begin, pair_end);
+  else
+    pair_materialize_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(
+        coords, values, n, tab, dp, use_dir, dist, diffs, (long long*)groups, mask, pair_begin, pair_end);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,753 @@
+"""Variogram: the reference's experimental-variogram API on top of the fused
+B200 pair kernels.
+
+Same constructor and properties as ``skgstat.Variogram`` (Variogram.py:31-48)
+for the path BASELINE.json names: ``Variogram(coordinates, values, estimator,
+model, dist_func, bin_func, normalize, fit_method, fit_sigma, use_nugget,
+maxlag, samples, n_lags, ...)`` with ``bins``, ``bin_count``, ``experimental``,
+``maxlag``, ``n_lags``, ``fit()``, ``describe()``, ``parameters`` and the cache
+invalidation contract of its setters.
+
+What differs underneath: nothing O(N^2) is ever stored.  ``maxlag='median'``,
+ratio maxlags and ``bin_func='uniform'`` get exact order statistics / the exact
+maximum from select sweeps (engine.sq_order_stats), lag edges are then formed
+with numpy's own arithmetic from those scalars (bit-identical edges), and
+``experimental`` / ``bin_count`` come from ONE fused sweep
+(engine.hist -> skg_pair_hist) or, for Dowd, from the per-lag median select
+(engine.dz_medians).  The materialising accessors (``distance``,
+``pairwise_diffs``, ``lag_groups()``, ``lag_classes()``) remain, produced on the
+device on demand.  The model fit is scipy ``curve_fit`` on n_lags points and
+stays on the CPU, as in the reference (Variogram.py:1584-1821).
+
+Out of scope, raising NotImplementedError rather than taking a slow path:
+``samples=`` (ProbabalisticMetricSpace), sparse ``max_dist`` spaces, non-euclidean
+metrics, cross/aggregate (2-D ``values``) variograms, clustering / histogram-rule
+binners, the genton/minmax/percentile/entropy estimators by name, ``fit_method='ml'``
+and harmonised models.
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+from collections.abc import Callable, Iterable
+
+import numpy as np
+from scipy.optimize import curve_fit
+
+from . import _lib, binning, estimators, models
+from ._exact import sq_threshold_bits
+from .MetricSpace import MetricSpace
+
+_GPU_ESTIMATORS = ("matheron", "cressie", "dowd")
+_GPU_BINNERS = ("even", "uniform")
+
+
+class Variogram:
+    def __init__(self, coordinates=None, values=None, estimator="matheron", model="spherical",
+                 dist_func="euclidean", bin_func="even", normalize=False, fit_method="trf",
+                 fit_sigma=None, use_nugget=False, maxlag=None, samples=None, n_lags=10,
+                 multivariate="cross", verbose=False, **kwargs):
+        self._process_group = kwargs.pop("process_group", None)
+        self._kwargs = dict(kwargs)
+        if samples is not None:
+            raise NotImplementedError(
+                "samples= (ProbabalisticMetricSpace) is out of scope: the dense sweep it "
+                "approximates is what the GPU path accelerates")
+        self._1d = False
+        if not isinstance(coordinates, MetricSpace):
+            c = np.asarray(coordinates)
+            if c.ndim < 2:  # Variogram.py:291-297
+                c = np.column_stack((c, np.zeros(len(c))))
+                self._1d = True
+            coordinates = MetricSpace(c.copy(), dist_func, None)
+        elif dist_func != coordinates.dist_metric:
+            raise AttributeError("Distance metric of variogram differs from distance metric "
+                                 "of coordinates")
+        self._X = coordinates
+        self.multivariate = multivariate
+        self.verbose = verbose
+        self._reset_pair_state()
+        self._values = None
+        self.set_values(values)
+
+        self._n_lags_passed_value = n_lags
+        self._n_lags = None
+        self.n_lags = n_lags
+        self._maxlag = None
+        self.maxlag = maxlag
+
+        self._estimator = None
+        self._estimator_name = None
+        self.set_estimator(estimator)
+        self._bin_func_name = None
+        self._bin_func = None
+        self._bins = None
+        self.set_bin_func(bin_func)
+
+        self._use_nugget = None
+        self.use_nugget = use_nugget
+        self._model = None
+        self._model_name = None
+        self._is_model_custom = False
+        self.set_model(model)
+        self._normalized = normalize
+        self._fit_method = None
+        if fit_method is not None:
+            self.fit_method = fit_method
+        self._fit_sigma = None
+        self.fit_sigma = fit_sigma
+        self.cov = None
+        self.cof = None
+        self.fit(force=True, bounds=self._kwargs.get("fit_bounds"), p0=self._kwargs.get("fit_p0"))
+
+    # ------------------------------------------------------------------ state
+    def _reset_pair_state(self):
+        """Drop everything derived from (bins, values, mask): the reference resets
+        _groups/_bin_count/cof/cov in every setter (Variogram.py:885-940, 1274-1282)."""
+        self._groups = None
+        self._bin_count = None
+        self._exp = None
+        self.cof = None
+        self.cov = None
+
+    def _dirp(self):
+        """Directional mask parameters for the kernels (None = isotropic)."""
+        return None
+
+    def _dir_key(self):
+        return None
+
+    def _engine(self):
+        eng = self._X.engine(self._process_group)
+        if getattr(eng, "_values_owner", None) is not self or eng.values is None:
+            eng.set_values(self._values)
+            eng._values_owner = self
+        return eng
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_process_group"] = None
+        return st
+
+    # ------------------------------------------------------------- properties
+    @property
+    def coordinates(self):
+        return self._X.coords
+
+    @property
+    def metric_space(self):
+        return self._X
+
+    @property
+    def dim(self):
+        return 1 if self._1d else self.coordinates.shape[1]
+
+    @property
+    def values(self):
+        return self._values
+
+    @values.setter
+    def values(self, values):
+        self.set_values(values)
+
+    def set_values(self, values, calc_diff=True):
+        """Variogram.py:499-590 (1-D observations only)."""
+        if not len(values) == len(self.coordinates):
+            raise ValueError("The length of the values array has to match the length of "
+                             "coordinates")
+        y = np.asarray(values)
+        if y.ndim > 2:
+            raise ValueError("values has to be 1d (classic variogram) or 2d dimensional "
+                             "(cross-variogram)")
+        if y.ndim == 2:
+            raise NotImplementedError("cross / aggregate variograms (2-D values) are the next "
+                                      "row of the scope table, not built yet")
+        if len(set(y.flatten())) < 2:
+            warnings.warn("All input values are the same.")
+        self._values = y
+        self._diff = None
+        self._reset_pair_state()
+        eng = getattr(self._X, "_engine", None)
+        if eng is not None and getattr(eng, "_values_owner", None) is self:
+            eng._values_owner = None
+
+    @property
+    def is_cross_variogram(self):
+        return False
+
+    @property
+    def is_agg_variogram(self):
+        return False
+
+    @property
+    def n_lags(self):
+        if self._n_lags is None:
+            self._n_lags = len(self.bins)
+        return self._n_lags
+
+    @n_lags.setter
+    def n_lags(self, n):
+        if isinstance(n, str):
+            raise NotImplementedError("n_lags string values not implemented")
+        if isinstance(n, bool) or not isinstance(n, (int, np.integer)) or n < 1:
+            raise ValueError("n_lags has to be a positive integer")
+        if n > _lib.MAX_LAGS:
+            raise ValueError("n_lags > %d is not supported by the GPU lag table" % _lib.MAX_LAGS)
+        self._n_lags = int(n)
+        self._n_lags_passed_value = n
+        self._bins = None
+        self._reset_pair_state()
+
+    @property
+    def maxlag(self):
+        return self._maxlag
+
+    @maxlag.setter
+    def maxlag(self, value):
+        """Variogram.py:1274-1295."""
+        self._bins = None
+        self._reset_pair_state()
+        if value is None:
+            self._maxlag = None
+        elif isinstance(value, str):
+            if value == "median":
+                self._maxlag = self._distance_median()
+            elif value == "mean":
+                # np.mean sums the condensed vector pairwise in its storage order; the
+                # only way to get that exact value is to form the vector (as the reference)
+                self._maxlag = np.mean(self.distance)
+        elif value < 1:
+            self._maxlag = value * self._distance_max()
+        else:
+            self._maxlag = value
+
+    # ---- exact scalars of the distance distribution (never materialised) -----
+    def _distance_max(self, masked=False):
+        """np.max / np.nanmax of the (mask-passing) distances."""
+        dirp = self._dirp() if masked else None
+        key = ("dmax", self._dir_key() if masked else None)
+
+        def compute():
+            s = self._X.engine(self._process_group).sq_max(dirp)
+            return None if s is None else float(np.sqrt(np.float64(s)))
+
+        return self._X.cached(key, compute)
+
+    def _distance_order_stats(self, rank_fn, masked=False, limit=None):
+        dirp = self._dirp() if masked else None
+        eng = self._X.engine(self._process_group)
+        vals, total, max_s = eng.sq_order_stats(rank_fn, dirp=dirp, limit=limit)
+        if max_s is not None:
+            self._X._cache.setdefault(("dmax", self._dir_key() if masked else None),
+                                      float(np.sqrt(np.float64(max_s))))
+        return {r: float(np.sqrt(np.float64(s))) for r, s in vals.items()}, total
+
+    def _distance_median(self):
+        def compute():
+            d, total = self._distance_order_stats(
+                lambda t: [] if t == 0 else [(t - 1) // 2, t // 2])
+            if total == 0:
+                return np.nan
+            return binning.median_from_order_stats(total, lambda r: d[r])
+        return self._X.cached(("dmedian",), compute)
+
+    def _distance_percentile(self, q):
+        def compute():
+            d, total = self._distance_order_stats(
+                lambda t: [] if t == 0 else list(binning.percentile_ranks(t, q)[:2]))
+            if total == 0:
+                return np.nan
+            return binning.percentile_from_order_stats(total, q, lambda r: d[r])
+        return self._X.cached(("dpercentile", float(q)), compute)
+
+    # ------------------------------------------------------------------ binning
+    @property
+    def bin_func(self):
+        return self._bin_func
+
+    @bin_func.setter
+    def bin_func(self, bin_func):
+        self.set_bin_func(bin_func)
+
+    def set_bin_func(self, bin_func):
+        """Variogram.py:771-817."""
+        if isinstance(bin_func, str):
+            name = bin_func.lower()
+            if name not in _GPU_BINNERS:
+                if name in ("sturges", "scott", "fd", "sqrt", "doane", "kmeans", "ward",
+                            "stable_entropy"):
+                    raise NotImplementedError(
+                        "bin_func=%r needs every distance in host memory and is out of "
+                        "scope of the GPU path (even / uniform / callable / edges)" % bin_func)
+                raise ValueError("%r is not a valid estimator for `bins`" % bin_func)
+            self._bin_func = name
+            self._bin_func_name = bin_func
+            self._bins = None
+        elif isinstance(bin_func, Callable):
+            self._bin_func = bin_func
+            self._bin_func_name = "custom_func"
+            self._bins = None
+        elif isinstance(bin_func, Iterable):
+            edges = np.asarray(list(bin_func), dtype=float)
+            self._bin_func = None
+            self._bin_func_name = "custom_bin_edges"
+            self._bins = edges
+            self._maxlag = max(edges)
+            self._n_lags = len(edges)
+        else:
+            raise AttributeError("bin_func has to be of type string, iterable or callable.")
+        self._reset_pair_state()
+
+    def _calc_bins(self):
+        """Upper lag-class edges (binning.py:10-79; DirectionalVariogram.py:577-591)."""
+        n, maxlag = self._n_lags, self._maxlag
+        masked = self._dirp() is not None
+        if self._bin_func == "even":
+            dmax = self._distance_max(masked)
+            if dmax is None:
+                raise ValueError("no point pair passes the directional mask")
+            return binning.even_edges(n, maxlag, dmax), None
+        if self._bin_func == "uniform":
+            qs = [(i / n) * 100 for i in range(1, n + 1)]
+
+            def rank_fn(total):
+                if total == 0:
+                    return []
+                out = set()
+                for q in qs:
+                    out.update(binning.percentile_ranks(total, q)[:2])
+                return sorted(out)
+
+            d, total = self._distance_order_stats(rank_fn, masked=masked, limit=maxlag)
+            if total == 0:
+                raise ValueError("no point pair inside maxlag / the directional mask")
+            return np.fromiter((binning.percentile_from_order_stats(total, q, lambda r: d[r])
+                                for q in qs), dtype=float), None
+        # user callable: the reference's operator contract hands it the materialised vector
+        d = self.distance.copy()
+        if masked:
+            d[np.where(~self._direction_mask())] = np.nan
+        return self._bin_func(d, n, maxlag)
+
+    @property
+    def bins(self):
+        if self._bins is None:
+            edges, n = self._calc_bins()
+            self._bins = np.asarray(edges, dtype=float)
+            if n is not None:
+                self._n_lags = n
+        return self._bins.copy()
+
+    @bins.setter
+    def bins(self, bins):
+        self._bins = np.asarray(bins, dtype=float)
+        self._reset_pair_state()
+
+    # ---------------------------------------------------------------- estimator
+    @property
+    def estimator(self):
+        return self._estimator
+
+    @estimator.setter
+    def estimator(self, value):
+        self.set_estimator(value)
+
+    def set_estimator(self, estimator_name):
+        """Variogram.py:957-986."""
+        self._exp = None
+        self.cof, self.cov = None, None
+        if isinstance(estimator_name, str):
+            name = estimator_name.lower()
+            if name in _GPU_ESTIMATORS:
+                self._estimator = estimators.ESTIMATORS[name]
+                self._estimator_name = name
+            elif name in ("genton", "minmax", "percentile", "entropy"):
+                raise NotImplementedError(
+                    "estimator %r is outside the accelerated path (matheron, cressie, dowd); "
+                    "pass a callable to run it on materialised lag classes" % estimator_name)
+            else:
+                raise ValueError("Variogram estimator %s is not understood, please provide "
+                                 "the function." % estimator_name)
+        elif callable(estimator_name):
+            self._estimator = estimator_name
+            self._estimator_name = None
+        else:
+            raise ValueError("The estimator has to be a string or callable.")
+
+    def _calc_experimental(self):
+        if self._exp is not None:
+            return
+        edges = self.bins
+        thr = sq_threshold_bits(edges)
+        if np.any(thr[1:] < thr[:-1]):
+            raise ValueError("bins must be monotonically increasing")
+        eng = self._engine()
+        dirp = self._dirp()
+        name = self._estimator_name
+        if name == "matheron":
+            cnt, ssq, _ = eng.hist(edges, _lib.STAT_SUM_SQ, dirp, thr_bits=thr)
+            exp = estimators.finalize_matheron(cnt, ssq)
+        elif name == "cressie":
+            cnt, _, srt = eng.hist(edges, _lib.STAT_SUM_SQRT, dirp, thr_bits=thr)
+            exp = estimators.finalize_cressie(cnt, srt)
+        elif name == "dowd":
+            cnt, med = eng.dz_medians(edges, dirp, thr_bits=thr)
+            exp = estimators.finalize_dowd(cnt, med)
+        else:  # user callable on materialised lag classes (reference operator contract)
+            classes = list(self.lag_classes())
+            cnt = np.fromiter((c.size for c in classes), dtype=np.int64)
+            exp = np.fromiter(map(self._estimator, classes), dtype=float)
+        self._bin_count = np.asarray(cnt, dtype=np.int64)
+        self._exp = np.asarray(exp, dtype=float)
+
+    @property
+    def bin_count(self):
+        self._calc_experimental()
+        return self._bin_count
+
+    @property
+    def experimental(self):
+        self._calc_experimental()
+        return self._exp.copy()
+
+    @property
+    def _experimental(self):
+        return self.experimental
+
+    def get_empirical(self, bin_center=False):
+        edges = self.bins
+        if bin_center:
+            widths = np.diff(np.concatenate(([0.0], edges)))
+            edges = edges - widths / 2
+        return edges, self.experimental
+
+    # --------------------------------------------------- materialising accessors
+    @property
+    def distance(self):
+        """Condensed distance vector (Variogram.py:1202-1208); device-generated."""
+        return self._X.engine(self._process_group).materialize(("dist",))["dist"]
+
+    @property
+    def distance_matrix(self):
+        return self._X.dists
+
+    @property
+    def pairwise_diffs(self):
+        if self._diff is None:
+            self._diff = self._engine().materialize(("diffs",))["diffs"]
+        return self._diff
+
+    @property
+    def value_matrix(self):
+        from scipy.spatial.distance import squareform  # layout helper only
+        return squareform(self.pairwise_diffs, checks=False)
+
+    def _direction_mask(self):
+        return np.ones(self._X.engine(self._process_group).n_pairs, dtype=bool)
+
+    def lag_groups(self):
+        """Lag class of every pair, -1 outside (Variogram.py:1989-2006)."""
+        if self._groups is None:
+            out = self._engine().materialize(("groups",), edges=self.bins, dirp=self._dirp())
+            self._groups = out["groups"]
+        return self._groups
+
+    def lag_classes(self):
+        diffs = self.pairwise_diffs
+        groups = self.lag_groups()
+        for i in range(len(self.bins)):
+            yield diffs[np.where(groups == i)]
+
+    def preprocessing(self, force=False):
+        """Variogram.py:1559-1582: (re)compute bins and per-lag statistics."""
+        if force:
+            self._exp = None
+            self._bin_count = None
+            self._groups = None
+        self._calc_experimental()
+
+    # -------------------------------------------------------------------- model
+    @property
+    def model(self):
+        return self._model
+
+    @model.setter
+    def model(self, value):
+        self.set_model(value)
+
+    def set_model(self, model_name):
+        """Variogram.py:996-1030 (single named model or a callable)."""
+        self.cof, self.cov = None, None
+        if isinstance(model_name, str):
+            name = model_name.lower()
+            if "+" in name or name == "harmonize":
+                raise NotImplementedError("sums of models / harmonize are CPU-side features "
+                                          "outside the accelerated path")
+            if name not in models.MODELS:
+                raise ValueError("The theoretical Variogram function %s is not understood, "
+                                 "please provide the function" % model_name)
+            self._model = models.MODELS[name]
+            self._model_name = name
+            self._is_model_custom = False
+        elif callable(model_name):
+            self._model = model_name
+            self._model_name = getattr(model_name, "__name__", "custom")
+            self._is_model_custom = True
+        else:
+            raise ValueError("model has to be a string or a callable")
+
+    @property
+    def use_nugget(self):
+        return self._use_nugget
+
+    @use_nugget.setter
+    def use_nugget(self, enable_nugget):
+        if not isinstance(enable_nugget, bool):
+            raise ValueError("use_nugget has to be of type bool.")
+        self._use_nugget = enable_nugget
+
+    @property
+    def normalized(self):
+        return self._normalized
+
+    @normalized.setter
+    def normalized(self, status):
+        self._normalized = status
+
+    @property
+    def dist_function(self):
+        return self._X.dist_metric
+
+    @property
+    def fit_method(self):
+        return self._fit_method
+
+    @fit_method.setter
+    def fit_method(self, method):
+        if method not in ("trf", "lm", "manual", None):
+            if method == "ml":
+                raise NotImplementedError("fit_method='ml' is not part of the accelerated path")
+            raise ValueError("fit method has to be one of ['trf', 'lm', 'manual']")
+        self._fit_method = method
+
+    @property
+    def fit_sigma(self):
+        """Variogram.py:1359-1458 (distance-derived weights)."""
+        s = self._fit_sigma
+        if s is None:
+            return None
+        if isinstance(s, (list, tuple, np.ndarray)):
+            if len(s) == len(self.bins):
+                return s
+            raise AttributeError("len(fit_sigma) != len(bins)")
+        w = self.bins / np.max(self.bins)
+        if s == "linear":
+            return w
+        if s == "exp":
+            return 1.0 / np.exp(1.0 / w)
+        if s == "sqrt":
+            return np.sqrt(w)
+        if s == "sq":
+            return w ** 2
+        raise ValueError("fit_sigma is not understood. It has to be an array or one of "
+                         "['linear', 'exp', 'sqrt', 'sq'].")
+
+    @fit_sigma.setter
+    def fit_sigma(self, sigma):
+        self._fit_sigma = sigma
+        self.cof, self.cov = None, None
+
+    def _fit_bounds(self, x, y):
+        """Upper bounds: range <= max(bins), sill <= max(experimental), shape limits
+        (Variogram.py:2137-2185)."""
+        b = [np.nanmax(x), np.nanmax(y)]
+        if self._model_name == "matern":
+            b.append(20.0)
+        elif self._model_name == "stable":
+            b.append(2.0)
+        if self.use_nugget:
+            b.append(0.99 * np.nanmax(y))
+        return b
+
+    def fit(self, force=False, method=None, sigma=None, bounds=None, p0=None, **kwargs):
+        """Least-squares fit of the theoretical model to (bins, experimental) on the CPU
+        (Variogram.py:1584-1821): n_lags points, scipy curve_fit."""
+        old = {} if self.cof is None else self.describe()
+        if force:
+            self.cof, self.cov = None, None
+        self.preprocessing(force=force)
+        if method is not None:
+            self.fit_method = method
+        if sigma is not None:
+            self.fit_sigma = sigma
+        if self._fit_method is None:
+            return
+        x = np.array(self.bins)
+        y = self.experimental
+        keep = ~np.isnan(y)
+        _x, _y = x[keep], y[keep]
+        if self._fit_method == "manual":
+            if kwargs.get("nugget", False):
+                self.use_nugget = True
+            r = kwargs.get("range", self._kwargs.get("fit_range", old.get("effective_range")))
+            s = kwargs.get("sill", self._kwargs.get("fit_sill", old.get("sill")))
+            if r is None or s is None:
+                raise AttributeError("For manual fitting, you need to pass the variogram "
+                                     "parameters either to fit or to the Variogram instance.\n"
+                                     "parameter need to be prefixed with fit_ if passed to "
+                                     "__init__.")
+            n = kwargs.get("nugget", self._kwargs.get("fit_nugget", old.get("nugget", 0.0)))
+            if self._model_name in ("stable", "matern"):
+                key = "shape" if self._model_name == "stable" else "smoothness"
+                s2 = kwargs.get("shape", self._kwargs.get("fit_shape", old.get(key, 2.0)))
+                self.cof = [r, s, s2, n]
+            else:
+                self.cof = [r, s, n]
+            return
+        if self._is_model_custom:
+            def wrapped(h, *args):
+                return self._model(h, *args)
+            if bounds is None or p0 is None:
+                raise ValueError("a custom model needs explicit fit bounds and p0")
+        else:
+            if self.use_nugget:
+                def wrapped(h, *args):
+                    return self._model(h, *args)
+            else:
+                def wrapped(h, *args):
+                    return self._model(h, *args, 0)
+            if bounds is None:
+                bounds = (0, self._fit_bounds(x, y))
+            if p0 is None:
+                p0 = np.asarray(bounds[1])
+        sig = self.fit_sigma
+        if sig is not None:
+            sig = np.asarray(sig)[keep]
+        if self._fit_method == "trf":
+            self.cof, self.cov = curve_fit(wrapped, _x, _y, method="trf", sigma=sig, p0=p0,
+                                           bounds=bounds, **kwargs)
+        else:
+            self.cof, self.cov = curve_fit(wrapped, _x, _y, method="lm", sigma=sig, p0=p0,
+                                           **kwargs)
+
+    def transform(self, x):
+        if self.cof is None:
+            self.fit(force=True)
+        return self.fitted_model(x)
+
+    @property
+    def fitted_model(self):
+        if self.cof is None:
+            self.fit(force=True)
+        return self.fitted_model_function(self._model, self.cof)
+
+    @classmethod
+    def fitted_model_function(cls, model, cof=None, **kw):
+        """Variogram.py:1870-1900: cof = [range, sill, (shape), (nugget if != 0)]."""
+        if cof is None:
+            cof = [kw["effective_range"], kw["sill"]]
+            if "smoothness" in kw:
+                cof.append(kw["smoothness"])
+            if "shape" in kw:
+                cof.append(kw["shape"])
+            if kw["nugget"] != 0:
+                cof.append(kw["nugget"])
+        if not callable(model):
+            model = models.MODELS[str(model).lower()]
+        cof = list(cof)
+
+        def fitted_model(x):
+            return model(x, *cof)
+
+        return fitted_model
+
+    def describe(self, short=False, flat=False):
+        """Variogram.py:2627-2758 (single model)."""
+        if self.cof is None:
+            self.fit(force=True)
+        if self.cof is None:
+            raise RuntimeError("the variogram is not fitted (fit_method=None)")
+        maxlag = np.nanmax(self.bins)
+        maxvar = np.nanmax(self.experimental)
+        cof = self.cof
+        rdict = dict(
+            model=self._model_name,
+            estimator=self._estimator_name or getattr(self._estimator, "__name__", "custom"),
+            dist_func=self.dist_function,
+            normalized_effective_range=cof[0] * maxlag,
+            normalized_sill=cof[1] * maxvar,
+            normalized_nugget=cof[-1] * maxvar if self.use_nugget else 0,
+            effective_range=cof[0],
+            sill=cof[1],
+            nugget=cof[-1] if self.use_nugget else 0,
+        )
+        if self._model_name == "matern":
+            rdict["smoothness"] = cof[2]
+        elif self._model_name == "stable":
+            rdict["shape"] = cof[2]
+        if not short:
+            params = dict(
+                estimator=rdict["estimator"], model=self._model_name, dist_func=str(self.dist_function),
+                bin_func=self._bin_func_name, normalize=self.normalized,
+                fit_method=self._fit_method, fit_sigma=self._fit_sigma,
+                use_nugget=self.use_nugget, maxlag=self.maxlag,
+                n_lags=self._n_lags_passed_value, verbose=self.verbose)
+            if flat:
+                rdict.update(params)
+                rdict.update(self._kwargs)
+            else:
+                rdict["params"] = params
+                rdict["kwargs"] = self._kwargs
+        return rdict
+
+    @property
+    def parameters(self):
+        d = self.describe()
+        if self._model_name == "matern":
+            return [d["effective_range"], d["sill"], d["smoothness"], d["nugget"]]
+        if self._model_name == "stable":
+            return [d["effective_range"], d["sill"], d["shape"], d["nugget"]]
+        return [d["effective_range"], d["sill"], d["nugget"]]
+
+    def data(self, n=100, force=False):
+        """Theoretical variogram on n lags in [0, max(bins)] (Variogram.py:2187-2241)."""
+        if self.cof is None or force:
+            self.fit(force=True)
+        x = np.linspace(0, np.nanmax(self.bins), n)
+        return x, self.fitted_model(x)
+
+    # --------------------------------------------------------- quality measures
+    @property
+    def model_residuals(self):
+        """experimental - model at the lag edges (Variogram.py:2243-2268)."""
+        exp = self.experimental
+        return np.fromiter(map(lambda a, b: a - b, self.fitted_model(self.bins), exp), float)
+
+    residuals = model_residuals
+
+    @property
+    def rmse(self):
+        exp, mod = self.experimental, self.fitted_model(self.bins)
+        return np.sqrt(np.nansum((mod - exp) ** 2) / len(mod))
+
+    @property
+    def mse(self):
+        return np.nanmean(np.power(self.model_residuals, 2))
+
+    @property
+    def mae(self):
+        return np.nanmean(np.abs(self.model_residuals))
+
+    @property
+    def nrmse(self):
+        return self.rmse / np.nanmean(self.experimental)
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def __repr__(self):
+        try:
+            r, s, n = self.parameters[0], self.parameters[1], self.parameters[-1]
+            return "< %s Semivariogram fitted to %d bins >" % (self._model_name, len(self.bins))
+        except Exception:
+            return "< Variogram (B200) >"

@@ -1,0 +1,517 @@
+"""PairEngine: device-resident point set + the pair-sweep entry points.
+
+Host orchestration only.  Every O(N^2) step runs in libskg_b200.so (hand-written
+sm_100a kernels) through the ctypes C ABI; torch provides device buffers,
+streams and (for N GPUs) the NCCL collectives.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import distributed as D
+from ._exact import INF_BITS, from_bits, sq_threshold_bits, to_bits
+from .select import exact_select
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("skgstat_b200 needs a CUDA device (B200 / sm_100a); "
+                           "there is no CPU fallback for the hot path")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _hptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def dir_params(model: str, azimuth_deg: float, tolerance_deg: float, bandwidth: float,
+               exclude_ambiguous: bool = True):
+    """[model id, np.radians(azimuth), np.radians(tolerance/2), bandwidth/2, policy] - the
+    quantities DirectionalVariogram._triangle/_compass compare against (:704-714).
+    policy 1: guard-band pairs are resolved on the host (PairEngine.ambiguous_pairs)."""
+    mid = {"triangle": _lib.DIR_TRIANGLE, "compass": _lib.DIR_COMPASS}[model]
+    return np.array([mid, np.radians(azimuth_deg), np.radians(tolerance_deg / 2),
+                     bandwidth / 2, 1.0 if exclude_ambiguous else 0.0], dtype=np.float64)
+
+
+def literal_mask(dx, dy, dirp):
+    """The reference's mask decision for explicit pair vectors, with the host's numpy
+    (DirectionalVariogram.py:398-413 angles, :704-714 _triangle, :776-782 _compass).
+    dx, dy = P_i - P_j (i < j).  Only used for the guard-band pairs."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ed = np.sqrt(dx * dx + dy * dy)
+        pos = np.arccos(dx / ed)
+        ang = np.where(dy >= 0, pos, -pos)
+        t = np.abs(ang + dirp[1])
+        a = np.where(t > np.pi, t - np.pi, t)
+        a = np.where(a > np.pi / 2, np.pi - a, a)
+        ok = a <= dirp[2]
+        if int(dirp[0]) == _lib.DIR_TRIANGLE:
+            ok &= dirp[3] >= np.abs(ed * np.sin(t))
+    return ok
+
+
+class PairEngine:
+    """Pair sweeps over one point set resident in HBM (SoA fp64)."""
+
+    def __init__(self, coords, values=None, device=None, group=None):
+        _require_cuda()
+        self.lib = _lib.load()
+        c = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
+        if c.ndim != 2 or c.shape[1] not in (2, 3):
+            raise ValueError("coords must be (N, 2) or (N, 3); got %r" % (c.shape,))
+        self.n, self.dim = int(c.shape[0]), int(c.shape[1])
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.group = group
+        self.rank, self.world = D.world(group)
+        self._host_coords = c
+        with torch.cuda.device(self.device):
+            self.coords = torch.from_numpy(np.ascontiguousarray(c.T)).to(self.device)
+        self.values = None
+        self._host_values = None
+        self._vmin = self._vmax = 0.0
+        if values is not None:
+            self.set_values(values)
+        self.n_tiles = _lib.num_tiles(self.n)
+        self.t0, self.t1 = D.shard_range(self.n_tiles, self.rank, self.world)
+        self._scratch = None
+        self._amb_cache = {}
+        self.n_ambiguous = 0
+        self.launches = 0  # kernels of this library enqueued (bench bookkeeping)
+
+    # ------------------------------------------------------------------ utils
+    @property
+    def n_pairs(self) -> int:
+        return self.n * (self.n - 1) // 2
+
+    def set_values(self, values):
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).ravel()
+        if v.size != self.n:
+            raise ValueError("values length %d != number of points %d" % (v.size, self.n))
+        self.values = torch.from_numpy(v).to(self.device)
+        self._host_values = v
+        finite = v[np.isfinite(v)]
+        self._vmin = float(finite.min()) if finite.size else 0.0
+        self._vmax = float(finite.max()) if finite.size else 0.0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _hist_scratch(self, n_lags):
+        need = int(self.lib.skg_pair_hist_scratch_bytes(int(n_lags)))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    def sq_upper_bound(self) -> float:
+        """A value >= every squared pair distance (bounding-box diagonal, padded)."""
+        ext = self._host_coords.max(axis=0) - self._host_coords.min(axis=0)
+        ub = float(np.sum(ext * ext)) * (1.0 + 1e-12)
+        return ub if ub > 0.0 else 1.0
+
+    # ------------------------------------------------- guard-band resolution
+    AMB_CAPACITY = 1 << 24
+
+    def ambiguous_pairs(self, dirp, all_tiles=False):
+        """Pairs (of this rank's tiles) inside the guard band of the directional decision
+        that PASS the reference's literal numpy formula.  The kernels exclude every
+        guard-band pair (policy 1); their contributions are added by the callers.
+        Returns (i, j) index arrays, or None for isotropic sweeps / policy 0."""
+        if dirp is None or dirp[4] == 0.0:
+            return None
+        t0, t1 = (0, self.n_tiles) if all_tiles else (self.t0, self.t1)
+        key = tuple(float(x) for x in dirp) + (t0, t1)
+        if key in self._amb_cache:
+            return self._amb_cache[key]
+        cap = self.AMB_CAPACITY
+        pi = torch.empty(cap, dtype=torch.int32, device=self.device)
+        pj = torch.empty(cap, dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_dir_ambiguous(
+                _ptr(self.coords), self.n, self.dim, _hptr(dirp), _ptr(pi), _ptr(pj), _ptr(cnt),
+                cap, t0, t1, self._stream())
+        _lib.check(rc, "skg_pair_dir_ambiguous")
+        self.launches += 1 if t1 > t0 else 0
+        got = int(cnt.item())
+        if got > cap:
+            raise RuntimeError(
+                "%d point pairs lie exactly on the directional decision boundary (more than "
+                "%d): lattice data with a round azimuth/tolerance; not supported" % (got, cap))
+        i = pi[:got].cpu().numpy().astype(np.int64)
+        j = pj[:got].cpu().numpy().astype(np.int64)
+        order = np.lexsort((j, i))  # deterministic regardless of atomics order
+        i, j = i[order], j[order]
+        c = self._host_coords
+        ok = literal_mask(c[i, 0] - c[j, 0], c[i, 1] - c[j, 1], dirp)
+        self._amb_cache[key] = (i[ok], j[ok])
+        self.n_ambiguous = got
+        return self._amb_cache[key]
+
+    def _amb_keys(self, amb):
+        """(bits of s, |dz|) of host-resolved pairs, with the kernels' arithmetic."""
+        i, j = amb
+        c = self._host_coords
+        dx = c[i, 0] - c[j, 0]
+        dy = c[i, 1] - c[j, 1]
+        s = dx * dx + dy * dy
+        if self.values is not None:
+            v = self._host_values
+            dz = np.abs(v[i] - v[j])
+        else:
+            dz = np.zeros(i.size)
+        return np.ascontiguousarray(s).view(np.uint64), dz
+
+    # ------------------------------------------------------------- K2 (fused)
+    def hist(self, edges: Sequence[float], stats: int = _lib.STAT_SUM_SQ, dirp=None,
+             thr_bits: Optional[np.ndarray] = None):
+        """Fused distance -> lag class -> estimator statistics for the given UPPER
+        edges.  Returns (count int64[n], sum_sq float64[n], sum_sqrt float64[n])."""
+        if self.values is None:
+            raise ValueError("values not set")
+        thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        nl = int(thr.size)
+        out = torch.zeros(3 * nl, dtype=torch.float64, device=self.device)
+        cnt = torch.zeros(nl, dtype=torch.int64, device=self.device)
+        scratch = self._hist_scratch(nl)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_hist(
+                _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), _hptr(thr),
+                nl, int(stats), _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
+                _ptr(scratch), scratch.numel(), self.t0, self.t1, self._stream())
+        _lib.check(rc, "skg_pair_hist")
+        self.launches += 2 if self.t1 > self.t0 else 0
+        out[:nl] = cnt.to(torch.float64)  # exact: counts < 2^53
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, dz = self._amb_keys(amb)
+            g = np.searchsorted(thr, s_bits, side="right")
+            keep = g < nl
+            extra = np.zeros(3 * nl)
+            np.add.at(extra, g[keep], 1.0)
+            if stats & _lib.STAT_SUM_SQ:
+                np.add.at(extra, nl + g[keep], dz[keep] * dz[keep])
+            if stats & _lib.STAT_SUM_SQRT:
+                np.add.at(extra, 2 * nl + g[keep], np.sqrt(dz[keep]))
+            out += torch.from_numpy(extra).to(self.device)
+        D.allreduce_sum_(out, self.group)  # the single collective of the fused pass
+        host = out.cpu().numpy()
+        return host[:nl].astype(np.int64), host[nl:2 * nl].copy(), host[2 * nl:].copy()
+
+    # ------------------------------------------------ K1/K3 (order statistics)
+    def _select_runner(self, key_kind, thr, dirp, n_buckets, collect_max=None):
+        nl = 0 if thr is None else int(thr.size)
+        nseg = max(nl, 1)
+        amb = self.ambiguous_pairs(dirp)
+        amb_seg = amb_key = None
+        if amb is not None and amb[0].size:
+            s_bits, dz = self._amb_keys(amb)
+            amb_seg = np.searchsorted(thr, s_bits, side="right") if nl else np.zeros(s_bits.size, np.int64)
+            amb_key = s_bits.view(np.float64) if key_kind == _lib.KEY_SQDIST else dz
+            ok = (amb_seg < nseg) & np.isfinite(amb_key)
+            amb_seg, amb_key = amb_seg[ok], np.ascontiguousarray(amb_key[ok])
+
+        def amb_slots(lo, hi, sc):
+            """(keys, slots) of the host-resolved pairs inside the current windows."""
+            kb = amb_key.view(np.uint64)
+            inside = (kb >= lo[amb_seg]) & (kb < hi[amb_seg])
+            k, g = amb_key[inside], amb_seg[inside]
+            t = (k - lo[g].view(np.float64)) * sc[g]
+            b = np.minimum(n_buckets - 1, np.where(t >= 9.0e18, n_buckets - 1, t).astype(np.int64))
+            return k, g * n_buckets + b
+
+        def run_hist(lo, hi, sc):
+            hist = torch.zeros(nseg * n_buckets, dtype=torch.int64, device=self.device)
+            mx = torch.zeros(1, dtype=torch.int64, device=self.device)
+            lo = np.ascontiguousarray(lo, dtype=np.uint64)
+            hi = np.ascontiguousarray(hi, dtype=np.uint64)
+            sc = np.ascontiguousarray(sc, dtype=np.float64)
+            with torch.cuda.device(self.device):
+                rc = self.lib.skg_pair_select_hist(
+                    _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
+                    _hptr(thr), nl, key_kind, _hptr(lo), _hptr(hi), _hptr(sc), n_buckets,
+                    _ptr(hist), _ptr(mx) if nl == 0 else None, self.t0, self.t1, self._stream())
+            _lib.check(rc, "skg_pair_select_hist")
+            self.launches += 1 if self.t1 > self.t0 else 0
+            if amb_key is not None and amb_key.size:
+                _, slots = amb_slots(lo, hi, sc)
+                extra = np.bincount(slots, minlength=nseg * n_buckets).astype(np.int64)
+                hist += torch.from_numpy(extra).to(self.device)
+                if nl == 0:
+                    mx = torch.maximum(mx, torch.tensor([int(amb_key.view(np.int64).max())],
+                                                        dtype=torch.int64, device=self.device))
+            D.allreduce_sum_(hist, self.group)
+            if nl == 0 and collect_max is not None:
+                D.allreduce_max_(mx, self.group)
+                collect_max.append(int(mx.item()))
+            return hist.cpu().numpy()
+
+        def run_gather(lo, hi, sc, bitmap, cap):
+            cap = int(cap)
+            keys = torch.empty(max(cap, 1), dtype=torch.float64, device=self.device)
+            slots = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
+            cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+            bm = torch.from_numpy(bitmap.view(np.int32)).to(self.device)
+            lo = np.ascontiguousarray(lo, dtype=np.uint64)
+            hi = np.ascontiguousarray(hi, dtype=np.uint64)
+            sc = np.ascontiguousarray(sc, dtype=np.float64)
+            with torch.cuda.device(self.device):
+                rc = self.lib.skg_pair_select_gather(
+                    _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
+                    _hptr(thr), nl, key_kind, _hptr(lo), _hptr(hi), _hptr(sc), n_buckets,
+                    _ptr(bm), _ptr(keys), _ptr(slots), _ptr(cnt), cap, self.t0, self.t1,
+                    self._stream())
+            _lib.check(rc, "skg_pair_select_gather")
+            self.launches += 1 if self.t1 > self.t0 else 0
+            got = int(cnt.item())
+            if got > cap:
+                raise RuntimeError("gather overflow: %d > %d" % (got, cap))
+            keys, slots = keys[:got], slots[:got]
+            if amb_key is not None and amb_key.size:
+                k, sl = amb_slots(lo, hi, sc)
+                hit = ((bitmap[sl >> 5] >> (sl & 31).astype(np.uint32)) & 1).astype(bool)
+                keys = torch.cat([keys, torch.from_numpy(k[hit]).to(self.device)])
+                slots = torch.cat([slots, torch.from_numpy(sl[hit].astype(np.uint32).view(np.int32))
+                                   .to(self.device)])
+            k = D.allgather_varlen(keys, self.group)
+            s = D.allgather_varlen(slots, self.group)
+            return k.cpu().numpy(), s.cpu().numpy().view(np.uint32).astype(np.int64)
+
+        return run_hist, run_gather
+
+    def _buckets_for(self, n_keys, nseg):
+        b = 1 << 12
+        while b < (1 << 22) and b * 4096 < n_keys // max(nseg, 1):
+            b <<= 1
+        while nseg * b > (1 << 24) and b > (1 << 8):
+            b >>= 1
+        return b
+
+    def sq_order_stats(self, rank_fn, dirp=None, limit: Optional[float] = None):
+        """Exact order statistics of the squared distances s of all (mask-passing)
+        pairs with fl(sqrt(s)) <= limit.  rank_fn(total) -> 0-based ranks.
+        Returns (dict rank -> s, total, max_s) where max_s is the largest s of all
+        mask-passing pairs (window ignored; None if there is no pair)."""
+        from ._exact import sq_upper_inclusive_bits
+        ub = self.sq_upper_bound()
+        hi_bits = to_bits(ub) + 1
+        if limit is not None:
+            hi_bits = min(hi_bits, sq_upper_inclusive_bits(limit))
+        nb = self._buckets_for(self.n_pairs, 1)
+        mx = []
+        rh, rg = self._select_runner(_lib.KEY_SQDIST, None, dirp, nb, collect_max=mx)
+        vals, totals = exact_select(1, [0], [hi_bits], nb, lambda g, t: rank_fn(t), rh, rg)
+        # max over the first pass only (later passes see sub-windows but the max is global)
+        max_bits = mx[0] if mx else 0
+        max_s = from_bits(max_bits) if totals[0] > 0 or max_bits > 0 else None
+        return vals[0], totals[0], max_s
+
+    def sq_max(self, dirp=None):
+        """Largest squared distance among the (mask-passing) pairs (None if no pair
+        passes): one sweep with an empty histogram window, i.e. no atomics."""
+        mx = torch.zeros(1, dtype=torch.int64, device=self.device)
+        hist = torch.zeros(1, dtype=torch.int64, device=self.device)
+        zero = np.zeros(1, dtype=np.uint64)
+        sc = np.zeros(1, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_select_hist(
+                _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), None, 0,
+                _lib.KEY_SQDIST, _hptr(zero), _hptr(zero), _hptr(sc), 1, _ptr(hist), _ptr(mx),
+                self.t0, self.t1, self._stream())
+        _lib.check(rc, "skg_pair_select_hist")
+        self.launches += 1 if self.t1 > self.t0 else 0
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, _ = self._amb_keys(amb)
+            s_bits = s_bits[s_bits <= INF_BITS]
+            if s_bits.size:
+                mx = torch.maximum(mx, torch.tensor([int(s_bits.max())], dtype=torch.int64,
+                                                    device=self.device))
+        D.allreduce_max_(mx, self.group)
+        bits = int(mx.item())
+        # bits == 0 means s == 0 for every pair or no pair at all; both give max d = 0 / none
+        return from_bits(bits) if bits > 0 else (0.0 if (self.n_pairs > 0 and dirp is None) else None)
+
+    def dz_medians(self, edges, dirp=None, thr_bits=None):
+        """Per lag class: (count, median |dz|) exactly as np.nanmedian would return
+        over the materialised lag class (estimators.py:178)."""
+        if self.values is None:
+            raise ValueError("values not set")
+        thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        nl = int(thr.size)
+        hi = to_bits(abs(self._vmax - self._vmin)) + 1  # fl(zmax - zmin) >= every |dz|
+        nb = self._buckets_for(self.n_pairs, nl)
+        rh, rg = self._select_runner(_lib.KEY_ABSDZ, thr, dirp, nb)
+
+        def rank_fn(g, tot):
+            if tot == 0:
+                return []
+            return [(tot - 1) // 2, tot // 2]
+
+        vals, totals = exact_select(nl, [0] * nl, [hi] * nl, nb, rank_fn, rh, rg)
+        med = np.full(nl, np.nan)
+        for g in range(nl):
+            t = totals[g]
+            if t:
+                a, b = vals[g][(t - 1) // 2], vals[g][t // 2]
+                # np.median: mean of the two middle elements (numpy _median -> mean)
+                med[g] = a if (t % 2) else (a + b) / 2.0
+        return np.asarray(totals, dtype=np.int64), med
+
+    # -------------------------------------------------------- materialisation
+    def materialize(self, want=("dist",), edges=None, dirp=None, chunk=1 << 24):
+        """Condensed arrays (Variogram.distance / pairwise_diffs / lag_groups /
+        direction mask) produced on the device in chunks and copied to the host."""
+        thr = None if edges is None else sq_threshold_bits(edges)
+        nl = 0 if thr is None else int(thr.size)
+        P = self.n_pairs
+        out = {}
+        if "dist" in want:
+            out["dist"] = np.empty(P, dtype=np.float64)
+        if "diffs" in want:
+            out["diffs"] = np.empty(P, dtype=np.float64)
+        if "groups" in want:
+            out["groups"] = np.empty(P, dtype=np.int64)
+        if "mask" in want:
+            out["mask"] = np.empty(P, dtype=np.uint8)
+        for k0 in range(0, P, chunk):
+            k1 = min(P, k0 + chunk)
+            m = k1 - k0
+            bufs = {}
+            if "dist" in want:
+                bufs["dist"] = torch.empty(m, dtype=torch.float64, device=self.device)
+            if "diffs" in want:
+                bufs["diffs"] = torch.empty(m, dtype=torch.float64, device=self.device)
+            if "groups" in want:
+                bufs["groups"] = torch.empty(m, dtype=torch.int64, device=self.device)
+            if "mask" in want:
+                bufs["mask"] = torch.empty(m, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = self.lib.skg_pair_materialize(
+                    _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
+                    _hptr(thr), nl, _ptr(bufs.get("dist")), _ptr(bufs.get("diffs")),
+                    _ptr(bufs.get("groups")), _ptr(bufs.get("mask")), k0, k1, self._stream())
+            _lib.check(rc, "skg_pair_materialize")
+            self.launches += 1
+            for name, b in bufs.items():
+                out[name][k0:k1] = b.cpu().numpy()
+        amb = self.ambiguous_pairs(dirp, all_tiles=True)
+        if amb is not None and amb[0].size and ("mask" in want or "groups" in want):
+            i, j = amb
+            k = self.n * i - i * (i + 1) // 2 + (j - i - 1)
+            if "mask" in want:
+                out["mask"][k] = 1
+            if "groups" in want:
+                s_bits, _ = self._amb_keys(amb)
+                g = np.searchsorted(thr, s_bits, side="right")
+                out["groups"][k] = np.where(g >= nl, -1, g)
+        return out
+
+
+class KrigeEngine:
+    """Batched ordinary kriging over one sample set resident in HBM."""
+
+    CELL_TARGET = 4.0  # samples per grid cell aimed for
+
+    def __init__(self, coords, values, radius: float, device=None, group=None):
+        _require_cuda()
+        self.lib = _lib.load()
+        c = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
+        if c.ndim != 2 or c.shape[1] not in (2, 3):
+            raise ValueError("coords must be (N, 2) or (N, 3); got %r" % (c.shape,))
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).ravel()
+        if v.size != c.shape[0]:
+            raise ValueError("values length does not match coordinates")
+        self.n, self.dim = int(c.shape[0]), int(c.shape[1])
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.group = group
+        self.rank, self.world = D.world(group)
+        self.radius = float(radius)
+        self.launches = 0
+        self.grid = self._grid_params(c, self.radius)
+        ncell = int(self.grid[4] * self.grid[5] * self.grid[6])
+        with torch.cuda.device(self.device):
+            self.coords = torch.from_numpy(np.ascontiguousarray(c.T)).to(self.device)
+            self.values = torch.from_numpy(v).to(self.device)
+            self.cell_start = torch.empty(ncell + 1, dtype=torch.int32, device=self.device)
+            self.order = torch.empty(self.n, dtype=torch.int32, device=self.device)
+            scratch = torch.empty((ncell + self.n) * 4, dtype=torch.uint8, device=self.device)
+            rc = self.lib.skg_krige_build_grid(
+                _ptr(self.coords), self.n, self.dim, _hptr(self.grid), _ptr(self.cell_start),
+                _ptr(self.order), _ptr(scratch), scratch.numel(),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(rc, "skg_krige_build_grid")
+        self.launches += 4
+        self._scratch = torch.empty(16, dtype=torch.uint8, device=self.device)
+
+    @classmethod
+    def _grid_params(cls, c, radius):
+        lo, hi = c.min(axis=0), c.max(axis=0)
+        ext = hi - lo
+        pos = ext[ext > 0]
+        if pos.size:
+            h = float((np.prod(pos) * cls.CELL_TARGET / len(c)) ** (1.0 / pos.size))
+        else:
+            h = 1.0
+        if radius > 0 and np.isfinite(radius):
+            h = max(h, radius / 64.0)
+        h = max(h, float(ext.max()) / 2048.0, 1e-300)
+        dims = [int(np.floor(e / h)) + 1 for e in ext]
+        while np.prod([float(d) for d in dims]) > float(1 << 24):
+            h *= 1.5
+            dims = [int(np.floor(e / h)) + 1 for e in ext]
+        g = np.zeros(8, dtype=np.float64)
+        g[: len(lo)] = lo
+        g[3] = h
+        g[4], g[5] = dims[0], dims[1]
+        g[6] = dims[2] if len(dims) > 2 else 1
+        return g
+
+    def transform(self, targets, model: str, model_params, min_points: int, max_points: int):
+        """targets (M, dim) -> (z, sigma, status) numpy arrays for ALL M targets; with a
+        process group each rank krigs its contiguous slice and the slices are gathered."""
+        t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64))
+        if t.ndim != 2 or t.shape[1] != self.dim:
+            raise ValueError("targets must be (M, %d)" % self.dim)
+        m = int(t.shape[0])
+        mp = np.asarray(model_params, dtype=np.float64)
+        if mp.size != 4:
+            raise ValueError("model_params = [range, sill, shape, nugget]")
+        with torch.cuda.device(self.device):
+            tg = torch.from_numpy(np.ascontiguousarray(t.T)).to(self.device)
+            z, sigma, status = self.transform_device(tg, m, model, mp, min_points, max_points)
+            if self.world > 1:
+                b, e = D.shard_range(m, self.rank, self.world)
+                z = D.allgather_varlen(z[b:e], self.group)
+                sigma = D.allgather_varlen(sigma[b:e], self.group)
+                status = D.allgather_varlen(status[b:e], self.group)
+        return z.cpu().numpy(), sigma.cpu().numpy(), status.cpu().numpy()
+
+    def transform_device(self, targets_soa: torch.Tensor, m: int, model: str, mp: np.ndarray,
+                         min_points: int, max_points: int):
+        """Device-resident variant: targets_soa is a (dim*M) fp64 CUDA tensor; returns
+        device tensors (only this rank's slice [begin, end) is filled)."""
+        z = torch.full((m,), float("nan"), dtype=torch.float64, device=self.device)
+        sigma = torch.full((m,), float("nan"), dtype=torch.float64, device=self.device)
+        status = torch.zeros(m, dtype=torch.int32, device=self.device)
+        b, e = D.shard_range(m, self.rank, self.world)
+        mp = np.ascontiguousarray(mp, dtype=np.float64)
+        rc = self.lib.skg_krige(
+            _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(self.grid),
+            _ptr(self.cell_start), _ptr(self.order), _ptr(targets_soa), m,
+            _lib.MODEL_IDS[model], _hptr(mp), self.radius, int(min_points), int(max_points),
+            _ptr(z), _ptr(sigma), _ptr(status), _ptr(self._scratch), self._scratch.numel(),
+            b, e, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(rc, "skg_krige")
+        self.launches += 1 if e > b else 0
+        return z, sigma, status
