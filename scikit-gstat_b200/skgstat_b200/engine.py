@@ -24,6 +24,33 @@ def _require_cuda():
                            "there is no CPU fallback for the hot path")
 
 
+class Traffic:
+    """Host<->device byte counters of the current process (bench.py reads them)."""
+    h2d = 0
+    d2h = 0
+
+    @classmethod
+    def reset(cls):
+        cls.h2d = 0
+        cls.d2h = 0
+
+
+def to_device(a: np.ndarray, device) -> torch.Tensor:
+    """Host array -> device through pinned memory."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    Traffic.h2d += t.numel() * t.element_size()
+    try:
+        t = t.pin_memory()
+    except RuntimeError:
+        pass
+    return t.to(device, non_blocking=True)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    Traffic.d2h += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -75,7 +102,7 @@ class PairEngine:
         self.rank, self.world = D.world(group)
         self._host_coords = c
         with torch.cuda.device(self.device):
-            self.coords = torch.from_numpy(np.ascontiguousarray(c.T)).to(self.device)
+            self.coords = to_device(c.T, self.device)
         self.values = None
         self._host_values = None
         self._vmin = self._vmax = 0.0
@@ -97,7 +124,7 @@ class PairEngine:
         v = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).ravel()
         if v.size != self.n:
             raise ValueError("values length %d != number of points %d" % (v.size, self.n))
-        self.values = torch.from_numpy(v).to(self.device)
+        self.values = to_device(v, self.device)
         self._host_values = v
         finite = v[np.isfinite(v)]
         self._vmin = float(finite.min()) if finite.size else 0.0
@@ -147,8 +174,8 @@ class PairEngine:
             raise RuntimeError(
                 "%d point pairs lie exactly on the directional decision boundary (more than "
                 "%d): lattice data with a round azimuth/tolerance; not supported" % (got, cap))
-        i = pi[:got].cpu().numpy().astype(np.int64)
-        j = pj[:got].cpu().numpy().astype(np.int64)
+        i = to_host(pi[:got]).astype(np.int64)
+        j = to_host(pj[:got]).astype(np.int64)
         order = np.lexsort((j, i))  # deterministic regardless of atomics order
         i, j = i[order], j[order]
         c = self._host_coords
@@ -202,9 +229,9 @@ class PairEngine:
                 np.add.at(extra, nl + g[keep], dz[keep] * dz[keep])
             if stats & _lib.STAT_SUM_SQRT:
                 np.add.at(extra, 2 * nl + g[keep], np.sqrt(dz[keep]))
-            out += torch.from_numpy(extra).to(self.device)
+            out += to_device(extra, self.device)
         D.allreduce_sum_(out, self.group)  # the single collective of the fused pass
-        host = out.cpu().numpy()
+        host = to_host(out)
         return host[:nl].astype(np.int64), host[nl:2 * nl].copy(), host[2 * nl:].copy()
 
     # ------------------------------------------------ K1/K3 (order statistics)
@@ -245,7 +272,7 @@ class PairEngine:
             if amb_key is not None and amb_key.size:
                 _, slots = amb_slots(lo, hi, sc)
                 extra = np.bincount(slots, minlength=nseg * n_buckets).astype(np.int64)
-                hist += torch.from_numpy(extra).to(self.device)
+                hist += to_device(extra, self.device)
                 if nl == 0:
                     mx = torch.maximum(mx, torch.tensor([int(amb_key.view(np.int64).max())],
                                                         dtype=torch.int64, device=self.device))
@@ -253,14 +280,14 @@ class PairEngine:
             if nl == 0 and collect_max is not None:
                 D.allreduce_max_(mx, self.group)
                 collect_max.append(int(mx.item()))
-            return hist.cpu().numpy()
+            return to_host(hist)
 
         def run_gather(lo, hi, sc, bitmap, cap):
             cap = int(cap)
             keys = torch.empty(max(cap, 1), dtype=torch.float64, device=self.device)
             slots = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
             cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
-            bm = torch.from_numpy(bitmap.view(np.int32)).to(self.device)
+            bm = to_device(bitmap.view(np.int32), self.device)
             lo = np.ascontiguousarray(lo, dtype=np.uint64)
             hi = np.ascontiguousarray(hi, dtype=np.uint64)
             sc = np.ascontiguousarray(sc, dtype=np.float64)
@@ -279,12 +306,12 @@ class PairEngine:
             if amb_key is not None and amb_key.size:
                 k, sl = amb_slots(lo, hi, sc)
                 hit = ((bitmap[sl >> 5] >> (sl & 31).astype(np.uint32)) & 1).astype(bool)
-                keys = torch.cat([keys, torch.from_numpy(k[hit]).to(self.device)])
-                slots = torch.cat([slots, torch.from_numpy(sl[hit].astype(np.uint32).view(np.int32))
-                                   .to(self.device)])
+                keys = torch.cat([keys, to_device(k[hit], self.device)])
+                slots = torch.cat([slots, to_device(sl[hit].astype(np.uint32).view(np.int32),
+                                                     self.device)])
             k = D.allgather_varlen(keys, self.group)
             s = D.allgather_varlen(slots, self.group)
-            return k.cpu().numpy(), s.cpu().numpy().view(np.uint32).astype(np.int64)
+            return to_host(k), to_host(s).view(np.uint32).astype(np.int64)
 
         return run_hist, run_gather
 
@@ -403,7 +430,7 @@ class PairEngine:
             _lib.check(rc, "skg_pair_materialize")
             self.launches += 1
             for name, b in bufs.items():
-                out[name][k0:k1] = b.cpu().numpy()
+                out[name][k0:k1] = to_host(b)
         amb = self.ambiguous_pairs(dirp, all_tiles=True)
         if amb is not None and amb[0].size and ("mask" in want or "groups" in want):
             i, j = amb
@@ -441,8 +468,8 @@ class KrigeEngine:
         self.grid = self._grid_params(c, self.radius)
         ncell = int(self.grid[4] * self.grid[5] * self.grid[6])
         with torch.cuda.device(self.device):
-            self.coords = torch.from_numpy(np.ascontiguousarray(c.T)).to(self.device)
-            self.values = torch.from_numpy(v).to(self.device)
+            self.coords = to_device(c.T, self.device)
+            self.values = to_device(v, self.device)
             self.cell_start = torch.empty(ncell + 1, dtype=torch.int32, device=self.device)
             self.order = torch.empty(self.n, dtype=torch.int32, device=self.device)
             scratch = torch.empty((ncell + self.n) * 4, dtype=torch.uint8, device=self.device)
@@ -488,14 +515,14 @@ class KrigeEngine:
         if mp.size != 4:
             raise ValueError("model_params = [range, sill, shape, nugget]")
         with torch.cuda.device(self.device):
-            tg = torch.from_numpy(np.ascontiguousarray(t.T)).to(self.device)
+            tg = to_device(t.T, self.device)
             z, sigma, status = self.transform_device(tg, m, model, mp, min_points, max_points)
             if self.world > 1:
                 b, e = D.shard_range(m, self.rank, self.world)
                 z = D.allgather_varlen(z[b:e], self.group)
                 sigma = D.allgather_varlen(sigma[b:e], self.group)
                 status = D.allgather_varlen(status[b:e], self.group)
-        return z.cpu().numpy(), sigma.cpu().numpy(), status.cpu().numpy()
+        return to_host(z), to_host(sigma), to_host(status)
 
     def transform_device(self, targets_soa: torch.Tensor, m: int, model: str, mp: np.ndarray,
                          min_points: int, max_points: int):
