@@ -11,7 +11,7 @@ namespace skg {
 constexpr int TILE = SKG_TILE;  // points per tile edge
 constexpr int BLOCK = 128;      // threads per CTA in the pair sweeps
 constexpr int RI = TILE / BLOCK;  // i-points held in registers per thread
-constexpr int LUT_MAX = 2048;
+constexpr int LUT_MAX = 1024;
 constexpr int THR_MAX = SKG_MAX_LAGS + 6;
 constexpr uint64_t INF_BITS = 0x7FF0000000000000ull;
 constexpr uint64_t NAN_BITS = 0x7FF8000000000000ull;

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -94,6 +95,14 @@ __device__ __forceinline__ void load_tables(const BinTable& tab, uint64_t* sThr,
 }
 
 // -------------------------------------------------------------- K2: hist ---
+//
+// The hot kernel.  CTA = HB threads, each thread keeps HR "i" points in
+// registers (HB*HR = TILE) and walks the "j" tile from shared memory.  Per-lag
+// accumulators are PRIVATE to the thread (acc[lag][tid], bank-conflict free, no
+// atomics): plain shared-memory read-modify-write.  The j tile and the lag tables
+// are STATIC shared arrays and the accumulators the only DYNAMIC one, so the
+// compiler knows accumulator stores cannot alias table/tile loads and is free to
+// hoist the next pairs' loads and fp64 math above them.
 
 struct HistPartial {  // one per (CTA, lag class)
   unsigned long long count;
@@ -101,101 +110,242 @@ struct HistPartial {  // one per (CTA, lag class)
   double sum_sqrt;
 };
 
-template <bool DIR, int STATS, bool PRIV>
-struct HistOp {
-  const uint64_t* sThr;
-  const uint8_t* sLut;
-  int key0, shift, ncell, emax, nb;
-  unsigned* cnt;  // PRIV: already offset by tid, stride BLOCK per class
-  double* sq;
-  double* rt;
-  const DirParams* dp;
-  __device__ __forceinline__ void pair(double s, double dx, double dy, double zi, double zj, int64_t, int64_t) {
-    const uint64_t sb = (uint64_t)__double_as_longlong(s);
-    const int g = find_bin(sb, sThr, sLut, key0, shift, ncell, emax);
-    if (g < nb) {
-      if (DIR) {
-        if (!dir_mask(dx, dy, s, *dp)) return;
-      }
-      const double dz = zi - zj;
-      if (PRIV) {
-        const int a = g * BLOCK;
-        cnt[a] += 1u;
-        if (STATS & SKG_STAT_SUM_SQ) sq[a] = fma(dz, dz, sq[a]);
-        if (STATS & SKG_STAT_SUM_SQRT) rt[a] += sqrt(fabs(dz));
-      } else {
-        atomicAdd(&cnt[g], 1u);
-        if (STATS & SKG_STAT_SUM_SQ) atomicAdd(&sq[g], dz * dz);
-        if (STATS & SKG_STAT_SUM_SQRT) atomicAdd(&rt[g], sqrt(fabs(dz)));
-      }
-    }
-  }
-};
+// Per-thread accumulator record in shared memory: {sum, count} (16 B) or
+// {sum_sq, count, sum_sqrt, pad} (32 B).  One predicated 128-bit load/store pair per
+// in-range pair of points; a warp's records for one lag class are contiguous, i.e.
+// bank-conflict free.  Written in PTX so that ptxas emits predicated LDS/STS instead
+// of a branch per pair.  No "memory" clobber on purpose: records are only touched
+// through these helpers between the two __syncthreads() that fence the accumulation.
+struct HistRec16 { double sum; unsigned long long cnt; };
+struct HistRec32 { double sq; unsigned long long cnt; double rt; unsigned long long pad; };
 
-// smem layout (dynamic): TileSmem | thr[THR_MAX] u64 | sq[nb*S] | rt[nb*S] | cnt[nb*S] | lut
-// with S = BLOCK (private per-thread accumulators) or 1 (shared + atomics).
-template <int DIM, bool DIR, int STATS, bool PRIV>
-__global__ void __launch_bounds__(BLOCK)
+template <int STATS>
+__device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
+  if (STATS == 3) {
+    const double rt = sqrt(fabs(dz));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 tb, cb, rb, pb;\n\t.reg .f64 t, u;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t"
+        "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
+        "@p ld.shared.v2.b64 {rb, pb}, [%0+16];\n\t"
+        "mov.b64 t, tb;\n\tmov.b64 u, rb;\n\t"
+        "fma.rn.f64 t, %1, %1, t;\n\t"
+        "add.rn.f64 u, u, %2;\n\t"
+        "add.u64 cb, cb, 1;\n\t"
+        "mov.b64 tb, t;\n\tmov.b64 rb, u;\n\t"
+        "@p st.shared.v2.b64 [%0], {tb, cb};\n\t"
+        "@p st.shared.b64 [%0+16], rb;\n\t}"
+        :: "r"(addr), "d"(dz), "d"(rt), "r"(pred));
+  } else if (STATS == 2) {
+    const double rt = sqrt(fabs(dz));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 tb, cb;\n\t.reg .f64 t;\n\t"
+        "setp.ne.s32 p, %2, 0;\n\t"
+        "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
+        "mov.b64 t, tb;\n\t"
+        "add.rn.f64 t, t, %1;\n\t"
+        "add.u64 cb, cb, 1;\n\t"
+        "mov.b64 tb, t;\n\t"
+        "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
+        :: "r"(addr), "d"(rt), "r"(pred));
+  } else if (STATS == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 tb, cb;\n\t.reg .f64 t;\n\t"
+        "setp.ne.s32 p, %2, 0;\n\t"
+        "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
+        "mov.b64 t, tb;\n\t"
+        "fma.rn.f64 t, %1, %1, t;\n\t"
+        "add.u64 cb, cb, 1;\n\t"
+        "mov.b64 tb, t;\n\t"
+        "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
+        :: "r"(addr), "d"(dz), "r"(pred));
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 cb;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "@p ld.shared.b64 cb, [%0+8];\n\t"
+        "add.u64 cb, cb, 1;\n\t"
+        "@p st.shared.b64 [%0+8], cb;\n\t}"
+        :: "r"(addr), "r"(pred));
+  }
+}
+
+constexpr int HB = 64;          // threads per CTA
+constexpr int HR = TILE / HB;   // i-points per thread
+
+template <int EMAX>
+__device__ __forceinline__ int lag_of(uint64_t sb, const uint64_t* sThr, const uint8_t* sLutBiased,
+                                      int shift, int klo, int khi, int emax) {
+  // cell = clamp(hi32 >> shift, klo, khi); sLutBiased = sLut - klo
+  const int k = (int)((uint32_t)(sb >> 32) >> shift);
+  int g = sLutBiased[min(max(k, klo), khi)];
+  if (EMAX > 0) {
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) g += (sb >= sThr[g]) ? 1 : 0;
+  } else {
+    for (int e = 0; e < emax; ++e) g += (sb >= sThr[g]) ? 1 : 0;
+  }
+  return g;
+}
+
+// PRIV: private per-thread records + software-pipelined loop (front end of pair set
+// jj+1 is issued before the read-modify-writes of pair set jj).
+// !PRIV (n_lags too large for private records): one shared record per lag + atomics.
+template <int DIM, bool DIR, int STATS, int EMAX, bool PRIV>
+__global__ void __launch_bounds__(HB)
 pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                  const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
                  HistPartial* __restrict__ partial, int64_t t0, int64_t t1) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<DIM>& sm = *reinterpret_cast<TileSmem<DIM>*>(smem_raw);
-  uint64_t* sThr = reinterpret_cast<uint64_t*>(smem_raw + sizeof(TileSmem<DIM>));
-  const int nb = tab.nb;
-  const int S = PRIV ? BLOCK : 1;
-  double* sSq = reinterpret_cast<double*>(sThr + THR_MAX);
-  double* sRt = sSq + ((STATS & SKG_STAT_SUM_SQ) ? nb * S : 0);
-  unsigned* sCnt = reinterpret_cast<unsigned*>(sRt + ((STATS & SKG_STAT_SUM_SQRT) ? nb * S : 0));
-  uint8_t* sLut = reinterpret_cast<uint8_t*>(sCnt + nb * S);
-  const int tid = threadIdx.x;
+  __shared__ double2 sXY[TILE + 2];
+  __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
+  __shared__ double sZ[TILE + 2];
+  __shared__ uint64_t sThr[THR_MAX];
+  __shared__ uint8_t sLut[LUT_MAX];
+  extern __shared__ __align__(16) unsigned char acc_raw[];
 
-  load_tables(tab, sThr, sLut);
-  for (int k = tid; k < nb * S; k += BLOCK) {
-    sCnt[k] = 0u;
-    if (STATS & SKG_STAT_SUM_SQ) sSq[k] = 0.0;
-    if (STATS & SKG_STAT_SUM_SQRT) sRt[k] = 0.0;
+  constexpr int REC = (STATS == 3) ? 32 : 16;
+  const int nb = tab.nb;
+  const int S = PRIV ? HB : 1;
+  const int tid = threadIdx.x;
+  const double qnan = __longlong_as_double(NAN_BITS);
+
+  for (int k = tid; k < THR_MAX; k += HB) sThr[k] = tab.thr[k];
+  for (int k = tid; k < tab.ncell; k += HB) sLut[k] = tab.lut[k];
+  {
+    unsigned long long* z = reinterpret_cast<unsigned long long*>(acc_raw);
+    for (int k = tid; k < nb * S * (REC / 8); k += HB) z[k] = 0ull;
+  }
+  if (tid == 0) {
+    sXY[TILE] = make_double2(qnan, qnan);
+    sXY[TILE + 1] = make_double2(qnan, qnan);
+    sZ[TILE] = 0.0; sZ[TILE + 1] = 0.0;
+    if (DIM == 3) { sW[TILE] = qnan; sW[TILE + 1] = qnan; }
   }
   __syncthreads();
 
-  HistOp<DIR, STATS, PRIV> op;
-  op.sThr = sThr; op.sLut = sLut;
-  op.key0 = tab.key0; op.shift = tab.shift; op.ncell = tab.ncell; op.emax = tab.emax; op.nb = nb;
-  op.cnt = sCnt + (PRIV ? tid : 0);
-  op.sq = sSq + (PRIV ? tid : 0);
-  op.rt = sRt + (PRIV ? tid : 0);
-  op.dp = &dp;
-  sweep_tiles<DIM>(coords, values, n, t0, t1, sm, op);
+  const int shift = tab.shift, klo = tab.key0, khi = tab.key0 + tab.ncell - 1, emax = tab.emax;
+  const uint8_t* lutb = sLut - klo;
+  const unsigned aRec = (unsigned)__cvta_generic_to_shared(acc_raw) + (PRIV ? tid * REC : 0);
+  const int64_t nt = (n + TILE - 1) / TILE;
+  const double* __restrict__ X = coords;
+  const double* __restrict__ Y = coords + n;
+  const double* __restrict__ W = coords + 2 * n;
+
+  for (int64_t t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+    int I, J;
+    tile_decode(t, nt, I, J);
+    double xi[HR], yi[HR], wi[HR], zi[HR];
+#pragma unroll
+    for (int r = 0; r < HR; ++r) {
+      const int64_t i = (int64_t)I * TILE + r * HB + tid;
+      const bool v = i < n;
+      xi[r] = v ? X[i] : qnan;
+      yi[r] = v ? Y[i] : qnan;
+      wi[r] = (DIM == 3) ? (v ? W[i] : qnan) : 0.0;
+      zi[r] = v ? values[i] : 0.0;
+    }
+    __syncthreads();  // every read of the previous j tile is done
+    for (int k = tid; k < TILE; k += HB) {
+      const int64_t j = (int64_t)J * TILE + k;
+      const bool v = j < n;
+      sXY[k] = make_double2(v ? X[j] : qnan, v ? Y[j] : qnan);
+      if (DIM == 3) sW[k] = v ? W[j] : qnan;
+      sZ[k] = v ? values[j] : 0.0;
+    }
+    __syncthreads();
+    const int64_t jn = n - (int64_t)J * TILE;
+    const int jcount = jn < TILE ? (int)jn : TILE;
+
+    auto body = [&](auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
+      // front end of pair set jj: lag classes g[] (nb = not accumulated) and dz[]
+      auto front = [&](int jj, int (&g)[HR], double (&dz)[HR]) {
+        const double2 pj = sXY[jj];
+        const double zj = sZ[jj];
+        const double wj = (DIM == 3) ? sW[jj] : 0.0;
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          const double dx = xi[r] - pj.x;
+          const double dy = yi[r] - pj.y;
+          double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (DIM == 3) {
+            const double dw = wi[r] - wj;
+            s = __dadd_rn(s, __dmul_rn(dw, dw));
+          }
+          const uint64_t sb = (uint64_t)__double_as_longlong(s);
+          int gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
+          if (DIAG) gg = (jj <= r * HB + tid) ? nb : gg;  // keep i < j only
+          if (DIR) {
+            if (gg < nb && !dir_mask(dx, dy, s, dp)) gg = nb;
+          }
+          g[r] = gg;
+          dz[r] = zi[r] - zj;
+        }
+      };
+      auto accumulate = [&](const int (&g)[HR], const double (&dz)[HR]) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          const int in = g[r] < nb ? 1 : 0;
+          if (PRIV) {
+            rmw_record<STATS>(aRec + (unsigned)g[r] * (unsigned)(HB * REC), dz[r], in);
+          } else if (in) {
+            unsigned char* rec = acc_raw + g[r] * REC;
+            atomicAdd(reinterpret_cast<unsigned long long*>(rec + 8), 1ull);
+            if (STATS & SKG_STAT_SUM_SQ) atomicAdd(reinterpret_cast<double*>(rec), dz[r] * dz[r]);
+            if (STATS & SKG_STAT_SUM_SQRT)
+              atomicAdd(reinterpret_cast<double*>(rec + (STATS == 3 ? 16 : 0)), sqrt(fabs(dz[r])));
+          }
+        }
+      };
+      int gA[HR], gB[HR];
+      double dA[HR], dB[HR];
+      front(0, gA, dA);
+      int jj = 1;
+      for (; jj + 1 <= jcount; jj += 2) {  // entries >= jcount are NaN-padded -> class nb
+        front(jj, gB, dB);
+        accumulate(gA, dA);
+        front(jj + 1, gA, dA);
+        accumulate(gB, dB);
+      }
+      if (jj <= jcount) {
+        front(jj, gB, dB);
+        accumulate(gA, dA);
+      }
+    };
+    if (I == J) body(std::true_type{}); else body(std::false_type{});
+  }
   __syncthreads();
 
-  // fixed-order block reduction of the per-thread accumulators
+  // fixed-order block reduction of the per-thread records
   HistPartial* out = partial + (int64_t)blockIdx.x * nb;
   if (PRIV) {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int g = warp; g < nb; g += BLOCK / 32) {
+    for (int gI = warp; gI < nb; gI += HB / 32) {
       unsigned long long c = 0;
       double a = 0.0, b = 0.0;
 #pragma unroll
-      for (int k = 0; k < BLOCK / 32; ++k) {
-        const int idx = g * BLOCK + lane + 32 * k;
-        c += sCnt[idx];
-        if (STATS & SKG_STAT_SUM_SQ) a += sSq[idx];
-        if (STATS & SKG_STAT_SUM_SQRT) b += sRt[idx];
+      for (int k = 0; k < HB / 32; ++k) {
+        const unsigned char* rec = acc_raw + (size_t)(gI * HB + lane + 32 * k) * REC;
+        c += *reinterpret_cast<const unsigned long long*>(rec + 8);
+        if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(rec);
+        if (STATS & SKG_STAT_SUM_SQRT) b += *reinterpret_cast<const double*>(rec + (STATS == 3 ? 16 : 0));
       }
       c = warp_sum(c);
       if (STATS & SKG_STAT_SUM_SQ) a = warp_sum(a);
       if (STATS & SKG_STAT_SUM_SQRT) b = warp_sum(b);
       if (lane == 0) {
-        out[g].count = c;
-        out[g].sum_sq = a;
-        out[g].sum_sqrt = b;
+        out[gI].count = c;
+        out[gI].sum_sq = a;
+        out[gI].sum_sqrt = b;
       }
     }
   } else {
-    for (int g = tid; g < nb; g += BLOCK) {
-      out[g].count = sCnt[g];
-      out[g].sum_sq = (STATS & SKG_STAT_SUM_SQ) ? sSq[g] : 0.0;
-      out[g].sum_sqrt = (STATS & SKG_STAT_SUM_SQRT) ? sRt[g] : 0.0;
+    for (int gI = tid; gI < nb; gI += HB) {
+      const unsigned char* rec = acc_raw + (size_t)gI * REC;
+      out[gI].count = *reinterpret_cast<const unsigned long long*>(rec + 8);
+      out[gI].sum_sq = (STATS & SKG_STAT_SUM_SQ) ? *reinterpret_cast<const double*>(rec) : 0.0;
+      out[gI].sum_sqrt = (STATS & SKG_STAT_SUM_SQRT)
+                             ? *reinterpret_cast<const double*>(rec + (STATS == 3 ? 16 : 0)) : 0.0;
     }
   }
 }
@@ -487,57 +637,56 @@ static int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0,
   return 0;
 }
 
-constexpr int MAX_GRID_PER_SM = 8;
+constexpr int MAX_GRID_PER_SM = 16;
 
-static size_t hist_smem_bytes(int dim, int nb, int stats, bool priv) {
-  const size_t S = priv ? BLOCK : 1;
-  size_t b = (dim == 3 ? sizeof(TileSmem<3>) : sizeof(TileSmem<2>)) + THR_MAX * 8;
-  if (stats & SKG_STAT_SUM_SQ) b += (size_t)nb * S * 8;
-  if (stats & SKG_STAT_SUM_SQRT) b += (size_t)nb * S * 8;
-  b += (size_t)nb * S * 4;
-  b += LUT_MAX;
-  return b;
+static size_t hist_smem_bytes(int nb, int stats, bool priv) {
+  const size_t S = priv ? HB : 1;
+  return (size_t)nb * S * (stats == 3 ? 32 : 16);
 }
 
-template <int DIM, bool DIR, int STATS, bool PRIV>
-static int launch_hist(const double* coords, const double* values, int64_t n, const BinTable& tab,
-                       const DirParams& dp, HistPartial* partial, int max_blocks, int64_t t0,
-                       int64_t t1, size_t smem, cudaStream_t st, int* nblocks_out) {
-  auto kern = pair_hist_kernel<DIM, DIR, STATS, PRIV>;
-  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+struct HistLaunch {
+  const double* coords; const double* values; int64_t n;
+  const BinTable* tab; const DirParams* dp; HistPartial* partial;
+  int max_blocks; int64_t t0, t1; size_t smem; cudaStream_t st; int* nblocks_out;
+};
+
+template <int DIM, bool DIR, int STATS, int EMAX, bool PRIV>
+static int launch_hist(const HistLaunch& L) {
+  auto kern = pair_hist_kernel<DIM, DIR, STATS, EMAX, PRIV>;
+  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   int occ = 0;
-  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
-  if (occ < 1) { set_error("pair_hist kernel does not fit (smem=%zu)", smem); return SKG_E_UNSUPPORTED; }
+  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HB, L.smem));
+  if (occ < 1) { set_error("pair_hist kernel does not fit (smem=%zu)", L.smem); return SKG_E_UNSUPPORTED; }
   occ = std::min(occ, MAX_GRID_PER_SM);
-  int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, t1 - t0);
-  grid = std::min<int64_t>(grid, max_blocks);
-  *nblocks_out = (int)grid;
-  kern<<<(unsigned)grid, BLOCK, smem, st>>>(coords, values, n, tab, dp, partial, t0, t1);
+  int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, L.t1 - L.t0);
+  grid = std::min<int64_t>(grid, L.max_blocks);
+  *L.nblocks_out = (int)grid;
+  kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial, L.t0, L.t1);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int DIM, bool DIR, bool PRIV>
-static int dispatch_hist_stats(int stats, const double* coords, const double* values, int64_t n,
-                               const BinTable& tab, const DirParams& dp, HistPartial* partial,
-                               int max_blocks, int64_t t0, int64_t t1, size_t smem,
-                               cudaStream_t st, int* nb_out) {
+template <int DIM, bool DIR, int EMAX, bool PRIV>
+static int dispatch_hist_stats(int stats, const HistLaunch& L) {
   switch (stats) {
-    case 0: return launch_hist<DIM, DIR, 0, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
-    case 1: return launch_hist<DIM, DIR, 1, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
-    case 2: return launch_hist<DIM, DIR, 2, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
-    default: return launch_hist<DIM, DIR, 3, PRIV>(coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+    case 0: return launch_hist<DIM, DIR, 0, EMAX, PRIV>(L);
+    case 1: return launch_hist<DIM, DIR, 1, EMAX, PRIV>(L);
+    case 2: return launch_hist<DIM, DIR, 2, EMAX, PRIV>(L);
+    default: return launch_hist<DIM, DIR, 3, EMAX, PRIV>(L);
   }
 }
 
-template <bool PRIV>
-static int dispatch_hist(int dim, bool dir, int stats, const double* coords, const double* values,
-                         int64_t n, const BinTable& tab, const DirParams& dp, HistPartial* partial,
-                         int max_blocks, int64_t t0, int64_t t1, size_t smem, cudaStream_t st,
-                         int* nb_out) {
-  if (dim == 3) return dispatch_hist_stats<3, false, PRIV>(stats, coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
-  if (dir) return dispatch_hist_stats<2, true, PRIV>(stats, coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
-  return dispatch_hist_stats<2, false, PRIV>(stats, coords, values, n, tab, dp, partial, max_blocks, t0, t1, smem, st, nb_out);
+template <int EMAX, bool PRIV>
+static int dispatch_hist_dim(int dim, bool dir, int stats, const HistLaunch& L) {
+  if (dim == 3) return dispatch_hist_stats<3, false, EMAX, PRIV>(stats, L);
+  if (dir) return dispatch_hist_stats<2, true, EMAX, PRIV>(stats, L);
+  return dispatch_hist_stats<2, false, EMAX, PRIV>(stats, L);
+}
+
+static int dispatch_hist(bool priv, int emax, int dim, bool dir, int stats, const HistLaunch& L) {
+  if (!priv) return dispatch_hist_dim<0, false>(dim, dir, stats, L);
+  if (emax <= 1) return dispatch_hist_dim<1, true>(dim, dir, stats, L);
+  return dispatch_hist_dim<0, true>(dim, dir, stats, L);
 }
 
 template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER>
@@ -664,15 +813,14 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   const int max_blocks = sm_count() * MAX_GRID_PER_SM;
   HistPartial* partial = reinterpret_cast<HistPartial*>(scratch);
   int nblocks = 0;
-  size_t smem = hist_smem_bytes(dim, n_lags, stats, true);
-  if (smem <= 200 * 1024) {
-    rc = dispatch_hist<true>(dim, use_dir, stats, coords, values, n, tab, dp, partial, max_blocks,
-                             tile_begin, tile_end, smem, st, &nblocks);
-  } else {
-    smem = hist_smem_bytes(dim, n_lags, stats, false);
-    rc = dispatch_hist<false>(dim, use_dir, stats, coords, values, n, tab, dp, partial, max_blocks,
-                              tile_begin, tile_end, smem, st, &nblocks);
+  HistLaunch L{coords, values, n, &tab, &dp, partial, max_blocks, tile_begin, tile_end, 0, st, &nblocks};
+  bool priv = true;
+  L.smem = hist_smem_bytes(n_lags, stats, true);
+  if (L.smem > 180 * 1024) {
+    priv = false;
+    L.smem = hist_smem_bytes(n_lags, stats, false);
   }
+  rc = dispatch_hist(priv, tab.emax, dim, use_dir, stats, L);
   if (rc) return rc;
   pair_hist_reduce_kernel<<<(n_lags + 127) / 128, 128, 0, st>>>(
       partial, nblocks, n_lags, reinterpret_cast<unsigned long long*>(count),

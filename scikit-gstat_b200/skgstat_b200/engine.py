@@ -86,6 +86,34 @@ def literal_mask(dx, dy, dirp):
     return ok
 
 
+def morton_order(c: np.ndarray) -> np.ndarray:
+    """Permutation that sorts points along a Z-order curve over their bounding box.
+
+    The pair kernels give each lane of a warp one "i" point; with spatially sorted
+    points the lanes of a warp are neighbours, so for a given "j" point they fall into
+    the same or adjacent lag classes: the lag-table reads broadcast, the per-lag
+    accumulator traffic is skipped for whole warps outside maxlag.  Results do not
+    depend on the order (counts exactly, sums to rounding)."""
+    n, dim = c.shape
+    lo = c.min(axis=0)
+    ext = c.max(axis=0) - lo
+    ext[ext <= 0] = 1.0
+    bits = 21 if dim == 3 else 31
+    q = np.minimum(((c - lo) / ext * (2 ** bits - 1)), 2 ** bits - 1)
+    q = np.nan_to_num(q, nan=0.0).astype(np.uint64)
+
+    def spread(v, step):
+        out = np.zeros_like(v)
+        for b in range(bits):
+            out |= ((v >> np.uint64(b)) & np.uint64(1)) << np.uint64(step * b)
+        return out
+
+    key = np.zeros(n, dtype=np.uint64)
+    for k in range(dim):
+        key |= spread(q[:, k], dim) << np.uint64(k)
+    return np.argsort(key, kind="stable")
+
+
 class PairEngine:
     """Pair sweeps over one point set resident in HBM (SoA fp64)."""
 
@@ -100,9 +128,15 @@ class PairEngine:
             else torch.device(device)
         self.group = group
         self.rank, self.world = D.world(group)
-        self._host_coords = c
+        # sweeps run over a Z-order sorted copy; materialising accessors need the
+        # caller's order (condensed index) and use an unsorted copy made on demand
+        self.perm = morton_order(c) if self.n > 64 else np.arange(self.n)
+        self._orig_coords = c
+        self._host_coords = np.ascontiguousarray(c[self.perm])
+        self._coords_unsorted = None
+        self._values_unsorted = None
         with torch.cuda.device(self.device):
-            self.coords = to_device(c.T, self.device)
+            self.coords = to_device(self._host_coords.T, self.device)
         self.values = None
         self._host_values = None
         self._vmin = self._vmax = 0.0
@@ -124,6 +158,9 @@ class PairEngine:
         v = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).ravel()
         if v.size != self.n:
             raise ValueError("values length %d != number of points %d" % (v.size, self.n))
+        self._orig_values = v
+        self._values_unsorted = None
+        v = np.ascontiguousarray(v[self.perm])
         self.values = to_device(v, self.device)
         self._host_values = v
         finite = v[np.isfinite(v)]
@@ -178,9 +215,14 @@ class PairEngine:
         j = to_host(pj[:got]).astype(np.int64)
         order = np.lexsort((j, i))  # deterministic regardless of atomics order
         i, j = i[order], j[order]
+        # the reference orients every pair as P_a - P_b with a < b in the caller's order
+        oi, oj = self.perm[i], self.perm[j]
+        swap = oi > oj
+        a = np.where(swap, j, i)
+        b = np.where(swap, i, j)
         c = self._host_coords
-        ok = literal_mask(c[i, 0] - c[j, 0], c[i, 1] - c[j, 1], dirp)
-        self._amb_cache[key] = (i[ok], j[ok])
+        ok = literal_mask(c[a, 0] - c[b, 0], c[a, 1] - c[b, 1], dirp)
+        self._amb_cache[key] = (a[ok], b[ok])
         self.n_ambiguous = got
         return self._amb_cache[key]
 
@@ -401,6 +443,10 @@ class PairEngine:
         thr = None if edges is None else sq_threshold_bits(edges)
         nl = 0 if thr is None else int(thr.size)
         P = self.n_pairs
+        if self._coords_unsorted is None:
+            self._coords_unsorted = to_device(self._orig_coords.T, self.device)
+        if self._values_unsorted is None and self.values is not None:
+            self._values_unsorted = to_device(self._orig_values, self.device)
         out = {}
         if "dist" in want:
             out["dist"] = np.empty(P, dtype=np.float64)
@@ -424,7 +470,8 @@ class PairEngine:
                 bufs["mask"] = torch.empty(m, dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 rc = self.lib.skg_pair_materialize(
-                    _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
+                    _ptr(self._coords_unsorted), _ptr(self._values_unsorted), self.n, self.dim,
+                    _hptr(dirp),
                     _hptr(thr), nl, _ptr(bufs.get("dist")), _ptr(bufs.get("diffs")),
                     _ptr(bufs.get("groups")), _ptr(bufs.get("mask")), k0, k1, self._stream())
             _lib.check(rc, "skg_pair_materialize")
@@ -433,7 +480,7 @@ class PairEngine:
                 out[name][k0:k1] = to_host(b)
         amb = self.ambiguous_pairs(dirp, all_tiles=True)
         if amb is not None and amb[0].size and ("mask" in want or "groups" in want):
-            i, j = amb
+            i, j = self.perm[amb[0]], self.perm[amb[1]]  # caller's order, i < j by construction
             k = self.n * i - i * (i + 1) // 2 + (j - i - 1)
             if "mask" in want:
                 out["mask"][k] = 1
