@@ -195,7 +195,7 @@ template <int DIM, bool DIR, int STATS, int EMAX, bool PRIV>
 __global__ void __launch_bounds__(HB)
 pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                  const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
-                 HistPartial* __restrict__ partial, int64_t t0, int64_t t1) {
+                 HistPartial* __restrict__ partial, int64_t t0, int64_t t1, int js) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
@@ -215,12 +215,6 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
     unsigned long long* z = reinterpret_cast<unsigned long long*>(acc_raw);
     for (int k = tid; k < nb * S * (REC / 8); k += HB) z[k] = 0ull;
   }
-  if (tid == 0) {
-    sXY[TILE] = make_double2(qnan, qnan);
-    sXY[TILE + 1] = make_double2(qnan, qnan);
-    sZ[TILE] = 0.0; sZ[TILE + 1] = 0.0;
-    if (DIM == 3) { sW[TILE] = qnan; sW[TILE + 1] = qnan; }
-  }
   __syncthreads();
 
   const int shift = tab.shift, klo = tab.key0, khi = tab.key0 + tab.ncell - 1, emax = tab.emax;
@@ -231,7 +225,12 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
   const double* __restrict__ Y = coords + n;
   const double* __restrict__ W = coords + 2 * n;
 
-  for (int64_t t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+  // Work item = (tile, j-chunk): each tile's j range is cut into `js` chunks so that the
+  // static round-robin over the grid stays balanced when there are few tiles per CTA.
+  const int jchunk = TILE / js;
+  for (int64_t w = t0 * js + blockIdx.x; w < t1 * js; w += gridDim.x) {
+    const int64_t t = w / js;
+    const int jbeg = (int)(w - t * js) * jchunk;
     int I, J;
     tile_decode(t, nt, I, J);
     double xi[HR], yi[HR], wi[HR], zi[HR];
@@ -244,17 +243,18 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
       wi[r] = (DIM == 3) ? (v ? W[i] : qnan) : 0.0;
       zi[r] = v ? values[i] : 0.0;
     }
-    __syncthreads();  // every read of the previous j tile is done
-    for (int k = tid; k < TILE; k += HB) {
-      const int64_t j = (int64_t)J * TILE + k;
-      const bool v = j < n;
+    const int64_t jn = n - ((int64_t)J * TILE + jbeg);
+    const int jcount = jn < jchunk ? (jn > 0 ? (int)jn : 0) : jchunk;
+    __syncthreads();  // every read of the previous j chunk is done
+    for (int k = tid; k < jcount + 2; k += HB) {  // two NaN entries pad the pipeline tail
+      const int64_t j = (int64_t)J * TILE + jbeg + k;
+      const bool v = k < jcount;
       sXY[k] = make_double2(v ? X[j] : qnan, v ? Y[j] : qnan);
       if (DIM == 3) sW[k] = v ? W[j] : qnan;
       sZ[k] = v ? values[j] : 0.0;
     }
     __syncthreads();
-    const int64_t jn = n - (int64_t)J * TILE;
-    const int jcount = jn < TILE ? (int)jn : TILE;
+    if (jcount == 0) continue;
 
     auto body = [&](auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
@@ -274,7 +274,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
           }
           const uint64_t sb = (uint64_t)__double_as_longlong(s);
           int gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
-          if (DIAG) gg = (jj <= r * HB + tid) ? nb : gg;  // keep i < j only
+          if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
           if (DIR) {
             if (gg < nb && !dir_mask(dx, dy, s, dp)) gg = nb;
           }
@@ -350,22 +350,30 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
   }
 }
 
-__global__ void pair_hist_reduce_kernel(const HistPartial* __restrict__ partial, int nblocks, int nb,
-                                        unsigned long long* __restrict__ count,
-                                        double* __restrict__ sum_sq, double* __restrict__ sum_sqrt) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nb) return;
+// Folds the per-CTA partials in a FIXED order (one warp per lag class; lane l takes CTAs
+// l, l+32, ... in sequence, then a shuffle tree): bitwise reproducible results.
+__global__ void __launch_bounds__(32)
+pair_hist_reduce_kernel(const HistPartial* __restrict__ partial, int nblocks, int nb,
+                        unsigned long long* __restrict__ count, double* __restrict__ sum_sq,
+                        double* __restrict__ sum_sqrt) {
+  const int g = blockIdx.x, lane = threadIdx.x;
   unsigned long long c = 0;
   double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblocks; ++k) {
+#pragma unroll 4
+  for (int k = lane; k < nblocks; k += 32) {
     const HistPartial p = partial[(int64_t)k * nb + g];
     c += p.count;
     a += p.sum_sq;
     b += p.sum_sqrt;
   }
-  count[g] += c;
-  if (sum_sq) sum_sq[g] += a;
-  if (sum_sqrt) sum_sqrt[g] += b;
+  c = warp_sum(c);
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    count[g] += c;
+    if (sum_sq) sum_sq[g] += a;
+    if (sum_sqrt) sum_sqrt[g] += b;
+  }
 }
 
 // ------------------------------------------------- K1/K3: select passes ---
@@ -647,21 +655,44 @@ static size_t hist_smem_bytes(int nb, int stats, bool priv) {
 struct HistLaunch {
   const double* coords; const double* values; int64_t n;
   const BinTable* tab; const DirParams* dp; HistPartial* partial;
+  unsigned int* counter; unsigned long long* out_count; double* out_sq; double* out_rt;
   int max_blocks; int64_t t0, t1; size_t smem; cudaStream_t st; int* nblocks_out;
 };
 
 template <int DIM, bool DIR, int STATS, int EMAX, bool PRIV>
 static int launch_hist(const HistLaunch& L) {
   auto kern = pair_hist_kernel<DIM, DIR, STATS, EMAX, PRIV>;
-  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  int occ = 0;
-  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HB, L.smem));
+  static thread_local size_t cached_smem = (size_t)-1;
+  static thread_local int cached_occ = 0;
+  if (cached_smem != L.smem) {
+    SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_occ, kern, HB, L.smem));
+    cached_smem = L.smem;
+  }
+  int occ = cached_occ;
   if (occ < 1) { set_error("pair_hist kernel does not fit (smem=%zu)", L.smem); return SKG_E_UNSUPPORTED; }
   occ = std::min(occ, MAX_GRID_PER_SM);
-  int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, L.t1 - L.t0);
+  // pick (CTAs per SM, j-split) that keeps the static round-robin balanced
+  const int64_t tiles = L.t1 - L.t0;
+  const int sms = sm_count();
+  double best = -1.0;
+  int64_t grid = 1;
+  int js = 1;
+  for (int k = occ; k >= std::max(1, occ - 1); --k) {
+    for (int cand = 1; cand <= 16; cand *= 2) {
+      const int64_t items = tiles * cand;
+      const int64_t g = std::min<int64_t>((int64_t)sms * k, items);
+      const int64_t rounds = (items + g - 1) / g;
+      double eff = (double)items / ((double)g * (double)rounds);
+      eff *= (g >= (int64_t)sms * k) ? (0.92 + 0.08 * k / occ) : (double)g / ((double)sms * occ);
+      eff *= 1.0 - 0.012 * std::log2((double)cand);  // per-item staging overhead
+      if (eff > best) { best = eff; grid = g; js = cand; }
+    }
+  }
   grid = std::min<int64_t>(grid, L.max_blocks);
   *L.nblocks_out = (int)grid;
-  kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial, L.t0, L.t1);
+  kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial,
+                                             L.t0, L.t1, js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -783,7 +814,7 @@ int64_t skg_pair_num_tiles(int64_t n) {
 
 int64_t skg_pair_hist_scratch_bytes(int n_lags) {
   if (n_lags < 1) n_lags = 1;
-  return (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
+  return 256 + (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
 }
 
 int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim, const double* dir,
@@ -811,9 +842,14 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   cudaStream_t st = (cudaStream_t)stream;
   const bool use_dir = dp.model != SKG_DIR_NONE;
   const int max_blocks = sm_count() * MAX_GRID_PER_SM;
-  HistPartial* partial = reinterpret_cast<HistPartial*>(scratch);
+  unsigned int* counter = nullptr;
+  HistPartial* partial = reinterpret_cast<HistPartial*>(reinterpret_cast<unsigned char*>(scratch) + 256);
   int nblocks = 0;
-  HistLaunch L{coords, values, n, &tab, &dp, partial, max_blocks, tile_begin, tile_end, 0, st, &nblocks};
+  HistLaunch L{coords, values, n, &tab, &dp, partial, counter,
+               reinterpret_cast<unsigned long long*>(count),
+               (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr,
+               (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr,
+               max_blocks, tile_begin, tile_end, 0, st, &nblocks};
   bool priv = true;
   L.smem = hist_smem_bytes(n_lags, stats, true);
   if (L.smem > 180 * 1024) {
@@ -822,7 +858,7 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   }
   rc = dispatch_hist(priv, tab.emax, dim, use_dir, stats, L);
   if (rc) return rc;
-  pair_hist_reduce_kernel<<<(n_lags + 127) / 128, 128, 0, st>>>(
+  pair_hist_reduce_kernel<<<n_lags, 32, 0, st>>>(
       partial, nblocks, n_lags, reinterpret_cast<unsigned long long*>(count),
       (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr, (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr);
   SKG_CUDA(cudaGetLastError());

@@ -258,7 +258,7 @@ class PairEngine:
                 nl, int(stats), _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
                 _ptr(scratch), scratch.numel(), self.t0, self.t1, self._stream())
         _lib.check(rc, "skg_pair_hist")
-        self.launches += 2 if self.t1 > self.t0 else 0
+        self.launches += 1 if self.t1 > self.t0 else 0
         out[:nl] = cnt.to(torch.float64)  # exact: counts < 2^53
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
