@@ -43,6 +43,8 @@ _GPU_BINNERS = ("even", "uniform")
 
 
 class Variogram:
+    _token_counter = 0
+
     def __init__(self, coordinates=None, values=None, estimator="matheron", model="spherical",
                  dist_func="euclidean", bin_func="even", normalize=False, fit_method="trf",
                  fit_sigma=None, use_nugget=False, maxlag=None, samples=None, n_lags=10,
@@ -119,9 +121,11 @@ class Variogram:
 
     def _engine(self):
         eng = self._X.engine(self._process_group)
-        if getattr(eng, "_values_owner", None) is not self or eng.values is None:
+        # token, not a reference to self: no reference cycle, so device buffers are
+        # released as soon as the variogram goes away
+        if getattr(eng, "_values_owner", None) != self._values_token or eng.values is None:
             eng.set_values(self._values)
-            eng._values_owner = self
+            eng._values_owner = self._values_token
         return eng
 
     def __getstate__(self):
@@ -162,14 +166,14 @@ class Variogram:
         if y.ndim == 2:
             raise NotImplementedError("cross / aggregate variograms (2-D values) are the next "
                                       "row of the scope table, not built yet")
-        if len(set(y.flatten())) < 2:
+        flat = y.ravel()
+        if flat.size == 0 or bool(np.all(flat == flat[0])):  # len(set(values)) < 2, Variogram.py:575
             warnings.warn("All input values are the same.")
         self._values = y
+        self._values_token = (id(self), Variogram._token_counter)
+        Variogram._token_counter += 1
         self._diff = None
         self._reset_pair_state()
-        eng = getattr(self._X, "_engine", None)
-        if eng is not None and getattr(eng, "_values_owner", None) is self:
-            eng._values_owner = None
 
     @property
     def is_cross_variogram(self):

@@ -35,15 +35,37 @@ class Traffic:
         cls.d2h = 0
 
 
+_PINNED = {}
+
+
+def _pinned_like(t: torch.Tensor) -> torch.Tensor:
+    """Reusable pinned staging buffer (cudaHostAlloc per upload would dominate small calls)."""
+    key = (t.dtype, max(1, t.numel()))
+    buf = _PINNED.get(key)
+    if buf is None:
+        cap = 1 << max(12, int(t.numel() - 1).bit_length()) if t.numel() > 1 else 4096
+        key2 = (t.dtype, cap)
+        buf = _PINNED.get(key2)
+        if buf is None:
+            try:
+                buf = torch.empty(cap, dtype=t.dtype).pin_memory()
+            except RuntimeError:
+                buf = torch.empty(cap, dtype=t.dtype)
+            _PINNED[key2] = buf
+        _PINNED[key] = buf
+    return buf
+
+
 def to_device(a: np.ndarray, device) -> torch.Tensor:
-    """Host array -> device through pinned memory."""
+    """Host array -> device through (reused) pinned memory; returns a new device tensor."""
     t = torch.from_numpy(np.ascontiguousarray(a))
     Traffic.h2d += t.numel() * t.element_size()
-    try:
-        t = t.pin_memory()
-    except RuntimeError:
-        pass
-    return t.to(device, non_blocking=True)
+    if t.numel() == 0:
+        return t.to(device)
+    buf = _pinned_like(t)
+    stage = buf[: t.numel()].view(t.shape) if t.dim() > 1 else buf[: t.numel()]
+    stage.copy_(t)
+    return stage.to(device)  # synchronous w.r.t. the host: the staging buffer is reusable
 
 
 def to_host(t: torch.Tensor) -> np.ndarray:
@@ -99,19 +121,27 @@ def morton_order(c: np.ndarray) -> np.ndarray:
     ext = c.max(axis=0) - lo
     ext[ext <= 0] = 1.0
     bits = 21 if dim == 3 else 31
-    q = np.minimum(((c - lo) / ext * (2 ** bits - 1)), 2 ** bits - 1)
-    q = np.nan_to_num(q, nan=0.0).astype(np.uint64)
-
-    def spread(v, step):
-        out = np.zeros_like(v)
-        for b in range(bits):
-            out |= ((v >> np.uint64(b)) & np.uint64(1)) << np.uint64(step * b)
-        return out
-
+    with np.errstate(invalid="ignore"):
+        q = ((c - lo) * ((2 ** bits - 1) / ext)).astype(np.int64)  # NaN -> arbitrary cell
+    q = np.clip(q, 0, 2 ** bits - 1).astype(np.uint64)
+    u = np.uint64
     key = np.zeros(n, dtype=np.uint64)
     for k in range(dim):
-        key |= spread(q[:, k], dim) << np.uint64(k)
-    return np.argsort(key, kind="stable")
+        v = q[:, k].copy()
+        if dim == 2:  # spread 32 bits to even positions
+            v = (v | (v << u(16))) & u(0x0000FFFF0000FFFF)
+            v = (v | (v << u(8))) & u(0x00FF00FF00FF00FF)
+            v = (v | (v << u(4))) & u(0x0F0F0F0F0F0F0F0F)
+            v = (v | (v << u(2))) & u(0x3333333333333333)
+            v = (v | (v << u(1))) & u(0x5555555555555555)
+        else:  # spread 21 bits to every third position
+            v = (v | (v << u(32))) & u(0x1F00000000FFFF)
+            v = (v | (v << u(16))) & u(0x1F0000FF0000FF)
+            v = (v | (v << u(8))) & u(0x100F00F00F00F00F)
+            v = (v | (v << u(4))) & u(0x10C30C30C30C30C3)
+            v = (v | (v << u(2))) & u(0x1249249249249249)
+        key |= v << u(k)
+    return np.argsort(key)
 
 
 class PairEngine:
@@ -145,6 +175,7 @@ class PairEngine:
         self.n_tiles = _lib.num_tiles(self.n)
         self.t0, self.t1 = D.shard_range(self.n_tiles, self.rank, self.world)
         self._scratch = None
+        self._buffers = {}
         self._amb_cache = {}
         self.n_ambiguous = 0
         self.launches = 0  # kernels of this library enqueued (bench bookkeeping)
@@ -166,6 +197,14 @@ class PairEngine:
         finite = v[np.isfinite(v)]
         self._vmin = float(finite.min()) if finite.size else 0.0
         self._vmax = float(finite.max()) if finite.size else 0.0
+
+    def _buffer(self, name, numel, dtype):
+        """Persistent device scratch (avoids allocator round trips on every call)."""
+        buf = self._buffers.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+            self._buffers[name] = buf
+        return buf[:numel]
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -249,8 +288,8 @@ class PairEngine:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
         nl = int(thr.size)
-        out = torch.zeros(3 * nl, dtype=torch.float64, device=self.device)
-        cnt = torch.zeros(nl, dtype=torch.int64, device=self.device)
+        out = self._buffer("hist_out", 3 * nl, torch.float64).zero_()
+        cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
         scratch = self._hist_scratch(nl)
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_hist(
@@ -299,8 +338,8 @@ class PairEngine:
             return k, g * n_buckets + b
 
         def run_hist(lo, hi, sc):
-            hist = torch.zeros(nseg * n_buckets, dtype=torch.int64, device=self.device)
-            mx = torch.zeros(1, dtype=torch.int64, device=self.device)
+            hist = self._buffer("select_hist", nseg * n_buckets, torch.int64).zero_()
+            mx = self._buffer("select_max", 1, torch.int64).zero_()
             lo = np.ascontiguousarray(lo, dtype=np.uint64)
             hi = np.ascontiguousarray(hi, dtype=np.uint64)
             sc = np.ascontiguousarray(sc, dtype=np.float64)
@@ -326,9 +365,9 @@ class PairEngine:
 
         def run_gather(lo, hi, sc, bitmap, cap):
             cap = int(cap)
-            keys = torch.empty(max(cap, 1), dtype=torch.float64, device=self.device)
-            slots = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
-            cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+            keys = self._buffer("gather_keys", max(cap, 1), torch.float64)
+            slots = self._buffer("gather_slots", max(cap, 1), torch.int32)
+            cnt = self._buffer("gather_cnt", 1, torch.int64).zero_()
             bm = to_device(bitmap.view(np.int32), self.device)
             lo = np.ascontiguousarray(lo, dtype=np.uint64)
             hi = np.ascontiguousarray(hi, dtype=np.uint64)
