@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads, exports every symbol include/skg_b200.h declares, and
+rejects bad arguments without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from skgstat_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "skg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(skg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_present_and_loads():
+    assert os.path.exists(_lib.LIB_PATH), "build with make -C scikit-gstat_b200/csrc"
+    lib = _lib.load()
+    assert lib.skg_abi_version() == _lib.ABI_VERSION
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), "symbol %s missing from libskg_b200.so" % name
+        assert name in _lib.SIGNATURES, "%s has no ctypes signature in _lib.py" % name
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_tile_count_and_constants():
+    assert _lib.num_tiles(0) == 0 and _lib.num_tiles(1) == 0
+    assert _lib.num_tiles(2) == 1
+    assert _lib.num_tiles(256) == 1
+    assert _lib.num_tiles(257) == 3
+    assert _lib.num_tiles(20000) == 79 * 80 // 2
+    text = open(os.path.join(ROOT, "include", "skg_b200.h")).read()
+    assert "#define SKG_TILE %d" % _lib.TILE in text
+    assert "#define SKG_MAX_LAGS %d" % _lib.MAX_LAGS in text
+    assert "#define SKG_KRIGE_MAX_POINTS %d" % _lib.KRIGE_MAX_POINTS in text
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    thr = np.array([1, 2, 3], dtype=np.uint64)
+    rc = lib.skg_pair_hist(None, None, 10, 2, None, thr.ctypes.data_as(C.c_void_p), 3, 1,
+                           None, None, None, None, 0, 0, 0, None)
+    assert rc == -1 and b"NULL" in lib.skg_last_error()
+    rc = lib.skg_pair_materialize(C.c_void_p(8), None, 10, 5, None, None, 0, None, None, None,
+                                  None, 0, 0, None)
+    assert rc == -2 and b"dim" in lib.skg_last_error()
+    rc = lib.skg_krige(None, None, 0, 2, None, None, None, None, 0, 0, None, 1.0, 1, 1, None, None,
+                       None, None, 0, 0, 0, None)
+    assert rc == -1
+    with pytest.raises(_lib.SkgError):
+        _lib.check(rc, "skg_krige")
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from skgstat_b200.engine import PairEngine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PairEngine(np.zeros((4, 2)))
+    import skgstat_b200 as skg
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        skg.Variogram(np.random.rand(10, 2), np.random.rand(10))
