@@ -131,7 +131,7 @@ __device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
         "mov.b64 t, tb;\n\tmov.b64 u, rb;\n\t"
         "fma.rn.f64 t, %1, %1, t;\n\t"
         "add.rn.f64 u, u, %2;\n\t"
-        "add.u64 cb, cb, 1;\n\t"
+        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
         "mov.b64 tb, t;\n\tmov.b64 rb, u;\n\t"
         "@p st.shared.v2.b64 [%0], {tb, cb};\n\t"
         "@p st.shared.b64 [%0+16], rb;\n\t}"
@@ -144,7 +144,7 @@ __device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
         "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
         "mov.b64 t, tb;\n\t"
         "add.rn.f64 t, t, %1;\n\t"
-        "add.u64 cb, cb, 1;\n\t"
+        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
         "mov.b64 tb, t;\n\t"
         "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
         :: "r"(addr), "d"(rt), "r"(pred));
@@ -155,7 +155,7 @@ __device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
         "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
         "mov.b64 t, tb;\n\t"
         "fma.rn.f64 t, %1, %1, t;\n\t"
-        "add.u64 cb, cb, 1;\n\t"
+        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
         "mov.b64 tb, t;\n\t"
         "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
         :: "r"(addr), "d"(dz), "r"(pred));
@@ -164,7 +164,7 @@ __device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
         "{\n\t.reg .pred p;\n\t.reg .b64 cb;\n\t"
         "setp.ne.s32 p, %1, 0;\n\t"
         "@p ld.shared.b64 cb, [%0+8];\n\t"
-        "add.u64 cb, cb, 1;\n\t"
+        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
         "@p st.shared.b64 [%0+8], cb;\n\t}"
         :: "r"(addr), "r"(pred));
   }
@@ -177,13 +177,18 @@ template <int EMAX>
 __device__ __forceinline__ int lag_of(uint64_t sb, const uint64_t* sThr, const uint8_t* sLutBiased,
                                       int shift, int klo, int khi, int emax) {
   // cell = clamp(hi32 >> shift, klo, khi); sLutBiased = sLut - klo
+  // Non-negative doubles order like their bit patterns, so the threshold test is done
+  // as ONE fp64 compare (the FP64 pipe has slack, the integer pipe does not); NaN (padded
+  // or excluded pairs) compares false and lands in class nb through the top LUT cell.
   const int k = (int)((uint32_t)(sb >> 32) >> shift);
   int g = sLutBiased[min(max(k, klo), khi)];
+  const double s = __longlong_as_double((long long)sb);
+  const double* dThr = reinterpret_cast<const double*>(sThr);
   if (EMAX > 0) {
 #pragma unroll
-    for (int e = 0; e < EMAX; ++e) g += (sb >= sThr[g]) ? 1 : 0;
+    for (int e = 0; e < EMAX; ++e) g += (s >= dThr[g]) ? 1 : 0;
   } else {
-    for (int e = 0; e < emax; ++e) g += (sb >= sThr[g]) ? 1 : 0;
+    for (int e = 0; e < emax; ++e) g += (s >= dThr[g]) ? 1 : 0;
   }
   return g;
 }
@@ -326,7 +331,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
 #pragma unroll
       for (int k = 0; k < HB / 32; ++k) {
         const unsigned char* rec = acc_raw + (size_t)(gI * HB + lane + 32 * k) * REC;
-        c += *reinterpret_cast<const unsigned long long*>(rec + 8);
+        c += *reinterpret_cast<const unsigned int*>(rec + 8);  // per-thread counts stay < 2^32
         if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(rec);
         if (STATS & SKG_STAT_SUM_SQRT) b += *reinterpret_cast<const double*>(rec + (STATS == 3 ? 16 : 0));
       }
