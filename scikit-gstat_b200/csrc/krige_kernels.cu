@@ -172,7 +172,10 @@ struct KrigeArgs {
   int64_t t0, t1;
   int cap;           // candidate list capacity per warp
   int region_bytes;  // per-warp shared region (list, later the matrix)
+  int retry_only;    // LU kernel: only targets the Cholesky kernel marked KRIGE_RETRY
 };
+
+constexpr int KRIGE_RETRY = 3;  // internal: covariance matrix not positive definite in fp64
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
@@ -257,38 +260,19 @@ __device__ int prune_list(unsigned long long* keys, int* ids, int len, int k, in
   return out;
 }
 
+// Neighbour search of one warp for target (tx, ty, tw): fills keys[]/ids[] (shared, per
+// warp) with the <= max_points nearest samples within the radius and returns their number.
 template <int DIM>
-__global__ void __launch_bounds__(256)
-krige_kernel(const __grid_constant__ KrigeArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  const int maxp = a.max_points;
-  // per-warp layout: region | nbr coords [DIM][maxp] | nbr values [maxp] | rhs copy [maxp+1] | mult [maxp+1]
-  const int per_warp = a.region_bytes + (DIM + 1) * maxp * 8 + 2 * (maxp + 1) * 8;
-  unsigned char* base = smem_raw + (size_t)warp * per_warp;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
-  int* ids = reinterpret_cast<int*>(base + (size_t)a.cap * 8);
-  double* A = reinterpret_cast<double*>(base);
-  double* ncoord = reinterpret_cast<double*>(base + a.region_bytes);
-  double* nval = ncoord + DIM * maxp;
-  double* rhs = nval + maxp;
-  double* mult = rhs + (maxp + 1);
-
+__device__ __forceinline__ int find_neighbours(const KrigeArgs& a, double tx, double ty, double tw,
+                                               unsigned long long* keys, int* ids, int lane) {
   const double* __restrict__ X = a.coords;
   const double* __restrict__ Y = a.coords + a.n;
   const double* __restrict__ W = a.coords + 2 * a.n;
   const GridParams g = a.grid;
   const double inv_h = 1.0 / g.h;
   const int rmax = (int)ceil(a.radius * inv_h) + 1;
-  const double qnan = __longlong_as_double(NAN_BITS);
-
-  for (int64_t t = a.t0 + (int64_t)blockIdx.x * wpb + warp; t < a.t1; t += (int64_t)gridDim.x * wpb) {
-    const double tx = a.targets[t];
-    const double ty = a.targets[a.m + t];
-    const double tw = DIM == 3 ? a.targets[2 * a.m + t] : 0.0;
-    const int cx = cell_coord(tx, g.ox, inv_h);
+  const int maxp = a.max_points;
+  const int cx = cell_coord(tx, g.ox, inv_h);
     const int cy = cell_coord(ty, g.oy, inv_h);
     const int cz = DIM == 3 ? cell_coord(tw, g.oz, inv_h) : 0;
     int len = 0;
@@ -370,6 +354,43 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
     __syncwarp();
     if (len > maxp) len = prune_list(keys, ids, len, maxp, lane);
     __syncwarp();
+    return len;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+krige_kernel(const __grid_constant__ KrigeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int maxp = a.max_points;
+  // per-warp layout: region | nbr coords [DIM][maxp] | nbr values [maxp] | rhs copy [maxp+1] | mult [maxp+1]
+  const int per_warp = a.region_bytes + (DIM + 1) * maxp * 8 + 2 * (maxp + 1) * 8;
+  unsigned char* base = smem_raw + (size_t)warp * per_warp;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  int* ids = reinterpret_cast<int*>(base + (size_t)a.cap * 8);
+  double* A = reinterpret_cast<double*>(base);
+  double* ncoord = reinterpret_cast<double*>(base + a.region_bytes);
+  double* nval = ncoord + DIM * maxp;
+  double* rhs = nval + maxp;
+  double* mult = rhs + (maxp + 1);
+
+  const double* __restrict__ X = a.coords;
+  const double* __restrict__ Y = a.coords + a.n;
+  const double* __restrict__ W = a.coords + 2 * a.n;
+  const GridParams g = a.grid;
+  const double inv_h = 1.0 / g.h;
+  const int rmax = (int)ceil(a.radius * inv_h) + 1;
+  const double qnan = __longlong_as_double(NAN_BITS);
+
+  for (int64_t t = a.t0 + (int64_t)blockIdx.x * wpb + warp; t < a.t1; t += (int64_t)gridDim.x * wpb) {
+    if (a.retry_only && a.status[t] != KRIGE_RETRY) continue;
+    const double tx = a.targets[t];
+    const double ty = a.targets[a.m + t];
+    const double tw = DIM == 3 ? a.targets[2 * a.m + t] : 0.0;
+    const int len = find_neighbours<DIM>(a, tx, ty, tw, keys, ids, lane);
+    __syncwarp();
     const int nn = len;
     if (nn < a.min_points || nn < 1) {  // Kriging.py:579-580 LessPointsError
       if (lane == 0) {
@@ -415,22 +436,39 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
     }
     __syncwarp();
     const int npairs = nn * (nn - 1) / 2;
-    for (int p = lane; p < npairs; p += 32) {
-      // p -> (i, j), i < j, row-major upper triangle
-      int i = (int)((2.0 * nn - 1.0 - sqrt((2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * p)) * 0.5);
-      while (i > 0 && i * nn - i * (i + 1) / 2 > p) --i;
-      while ((i + 1) * nn - (i + 1) * (i + 2) / 2 <= p) ++i;
-      const int j = p - (i * nn - i * (i + 1) / 2) + i + 1;
-      const double dx = ncoord[i] - ncoord[j];
-      const double dy = ncoord[maxp + i] - ncoord[maxp + j];
-      double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      if (DIM == 3) {
-        const double dw = ncoord[2 * maxp + i] - ncoord[2 * maxp + j];
-        s = __dadd_rn(s, __dmul_rn(dw, dw));
+    for (int p0 = lane; p0 < npairs; p0 += 64) {
+      // two independent pairs per trip: their loads, sqrt and exp chains overlap
+      int pi[2], pj[2];
+      double gv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int p = min(p0 + 32 * q, npairs - 1);
+        // p -> (i, j), i < j, row-major upper triangle
+        int i = (int)((2.0 * nn - 1.0 - sqrt((2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * p)) * 0.5);
+        while (i > 0 && i * nn - i * (i + 1) / 2 > p) --i;
+        while ((i + 1) * nn - (i + 1) * (i + 2) / 2 <= p) ++i;
+        pi[q] = i;
+        pj[q] = p - (i * nn - i * (i + 1) / 2) + i + 1;
       }
-      const double gv = gamma_model(sqrt(s), a.model);  // Kriging.py:594, 652-654
-      A[i * LD + j] = gv;
-      A[j * LD + i] = gv;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = pi[q], j = pj[q];
+        const double dx = ncoord[i] - ncoord[j];
+        const double dy = ncoord[maxp + i] - ncoord[maxp + j];
+        double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (DIM == 3) {
+          const double dw = ncoord[2 * maxp + i] - ncoord[2 * maxp + j];
+          s = __dadd_rn(s, __dmul_rn(dw, dw));
+        }
+        gv[q] = gamma_model(sqrt(s), a.model);  // Kriging.py:594, 652-654
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (p0 + 32 * q < npairs) {
+          A[pi[q] * LD + pj[q]] = gv[q];
+          A[pj[q] * LD + pi[q]] = gv[q];
+        }
+      }
     }
     __syncwarp();
 
@@ -461,13 +499,38 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
       const double rp = 1.0 / A[k * LD + k];
       for (int i = k + 1 + lane; i < N; i += 32) mult[i] = A[i * LD + k] * rp;
       __syncwarp();
-      // rank-1 update of the trailing block, lanes over columns
-      const int ncol = LD - (k + 1);
-      for (int jb = 0; jb < ncol; jb += 32) {
-        const int j = k + 1 + jb + lane;
-        if (j < LD) {
-          const double u = A[k * LD + j];
-          for (int i = k + 1; i < N; ++i) A[i * LD + j] = fma(-mult[i], u, A[i * LD + j]);
+      // rank-1 update of the trailing block.  Lane owns columns j0, j0+32, j0+64 (those
+      // that exist) and walks the rows in batches of 4: all loads of a batch are issued
+      // before its FMAs/stores, so the shared-memory latency is paid once per batch, not
+      // once per element.
+      {
+        const int NC = N + 1;  // real columns (rhs included); padding columns are skipped
+        const int j0 = k + 1 + lane;
+        const bool c0 = j0 < NC, c1 = j0 + 32 < NC, c2 = j0 + 64 < NC;
+        const double u0 = c0 ? A[k * LD + j0] : 0.0;
+        const double u1 = c1 ? A[k * LD + j0 + 32] : 0.0;
+        const double u2 = c2 ? A[k * LD + j0 + 64] : 0.0;
+        if (c0) {
+          for (int i0 = k + 1; i0 < N; i0 += 4) {
+            double m[4], a0[4], a1[4], a2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = min(i0 + q, N - 1);
+              m[q] = mult[i];
+              a0[q] = A[i * LD + j0];
+              a1[q] = c1 ? A[i * LD + j0 + 32] : 0.0;
+              a2[q] = c2 ? A[i * LD + j0 + 64] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = i0 + q;
+              if (i < N) {
+                A[i * LD + j0] = fma(-m[q], u0, a0[q]);
+                if (c1) A[i * LD + j0 + 32] = fma(-m[q], u1, a1[q]);
+                if (c2) A[i * LD + j0 + 64] = fma(-m[q], u2, a2[q]);
+              }
+            }
+          }
         }
       }
       __syncwarp();
@@ -506,6 +569,210 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
   }
 }
 
+// ---------------------------------------------- covariance-form fast path ---
+//
+// The ordinary-kriging system  [G 1; 1' 0] [w; mu] = [g; 1]  with G_ij = gamma(d_ij),
+// G_ii = 0 (Kriging.py:594-614) is rewritten with C = c_t 11' - G, c = c_t 1 - g,
+// c_t = nugget + sill:   C w = c + mu 1,  1'w = 1.  C is the covariance matrix of the
+// (valid) model, symmetric positive definite, so it factors as L L' WITHOUT pivoting in
+// half the flops and half the memory of the LU of the indefinite system:
+//     y1 = L^-1 c,  y2 = L^-1 1,  mu = (1 - y2.y1) / (y2.y2),  w = L^-T (y1 + mu y2).
+// Same weights, Lagrange multiplier, z and sigma as the reference's inv(A).dot(b) up to
+// cond * eps.  If a pivot is not positive in fp64 (invalid / degenerate model) the
+// target is marked KRIGE_RETRY and the partial-pivot LU kernel solves the original system.
+// Packed storage: row i of L starts at i(i+1)/2; rows n and n+1 hold c and 1 and are
+// carried through the elimination, which performs the two forward solves for free.
+
+__device__ __forceinline__ int prow(int i, int n) {  // offset of packed row i (rows n, n+1: n entries)
+  return i <= n ? i * (i + 1) / 2 : n * (n + 1) / 2 + n;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int maxp = a.max_points;
+  // per-warp layout: region | nbr coords [DIM][maxp] | values | gamma(d_0i) | col [maxp+2] | x [maxp]
+  const int per_warp = a.region_bytes + (DIM + 3) * maxp * 8 + (maxp + 2) * 8;
+  unsigned char* base = smem_raw + (size_t)warp * per_warp;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  int* ids = reinterpret_cast<int*>(base + (size_t)a.cap * 8);
+  double* L = reinterpret_cast<double*>(base);
+  double* ncoord = reinterpret_cast<double*>(base + a.region_bytes);
+  double* nval = ncoord + DIM * maxp;
+  double* gvec = nval + maxp;
+  double* xv = gvec + maxp;
+  double* col = xv + maxp;
+
+  const double* __restrict__ X = a.coords;
+  const double* __restrict__ Y = a.coords + a.n;
+  const double* __restrict__ W = a.coords + 2 * a.n;
+  const double qnan = __longlong_as_double(NAN_BITS);
+  const double ct = a.model.b + a.model.c0;
+
+  for (int64_t t = a.t0 + (int64_t)blockIdx.x * wpb + warp; t < a.t1; t += (int64_t)gridDim.x * wpb) {
+    const double tx = a.targets[t];
+    const double ty = a.targets[a.m + t];
+    const double tw = DIM == 3 ? a.targets[2 * a.m + t] : 0.0;
+    const int nn = find_neighbours<DIM>(a, tx, ty, tw, keys, ids, lane);
+    __syncwarp();
+    if (nn < a.min_points || nn < 1) {  // Kriging.py:579-580 LessPointsError
+      if (lane == 0) {
+        a.z[t] = qnan;
+        a.sigma[t] = qnan;
+        a.status[t] = SKG_KRIGE_LESS_POINTS;
+      }
+      __syncwarp();
+      continue;
+    }
+    double kd[2];
+    int kid[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      kd[q] = e < nn ? __longlong_as_double((long long)keys[e]) : 0.0;
+      kid[q] = e < nn ? ids[e] : 0;
+    }
+    __syncwarp();
+    const int n = nn;
+    const int rowc = prow(n, n), rowo = prow(n + 1, n);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      if (e < n) {
+        ncoord[e] = X[kid[q]];
+        ncoord[maxp + e] = Y[kid[q]];
+        if (DIM == 3) ncoord[2 * maxp + e] = W[kid[q]];
+        nval[e] = a.values[kid[q]];
+        const double gv = gamma_model(kd[q], a.model);  // Kriging.py:611-613
+        gvec[e] = gv;
+        L[prow(e, n) + e] = ct;  // C_ii = c_t - 0 (zero diagonal of the gamma matrix, :600)
+        L[rowc + e] = ct - gv;
+        L[rowo + e] = 1.0;
+      }
+    }
+    __syncwarp();
+    const int npairs = n * (n - 1) / 2;
+    for (int p0 = lane; p0 < npairs; p0 += 64) {
+      int pi[2], pj[2];
+      double cv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int p = min(p0 + 32 * q, npairs - 1);
+        // p -> (j, i), i < j: packed strictly-lower index p = j(j-1)/2 + i
+        int j = (int)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+        while (j * (j - 1) / 2 > p) --j;
+        while ((j + 1) * j / 2 <= p) ++j;
+        pj[q] = j;
+        pi[q] = p - j * (j - 1) / 2;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = pi[q], j = pj[q];
+        const double dx = ncoord[i] - ncoord[j];
+        const double dy = ncoord[maxp + i] - ncoord[maxp + j];
+        double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (DIM == 3) {
+          const double dw = ncoord[2 * maxp + i] - ncoord[2 * maxp + j];
+          s = __dadd_rn(s, __dmul_rn(dw, dw));
+        }
+        cv[q] = ct - gamma_model(sqrt(s), a.model);  // Kriging.py:594, 652-654
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (p0 + 32 * q < npairs) L[prow(pj[q], n) + pi[q]] = cv[q];
+    }
+    __syncwarp();
+
+    // ---- Cholesky, rows n and n+1 (rhs) carried along ---------------------
+    bool bad = false;
+    const int nrows = n + 2;
+    for (int k = 0; k < n; ++k) {
+      const double akk = L[prow(k, n) + k];
+      if (!(akk > 0.0)) { bad = true; break; }
+      const double rd = 1.0 / sqrt(akk);
+      for (int i = k + 1 + lane; i < nrows; i += 32) {
+        const int o = prow(i, n) + k;
+        const double l = L[o] * rd;
+        L[o] = l;
+        col[i] = l;
+      }
+      if (lane == 0) L[prow(k, n) + k] = akk * rd;
+      __syncwarp();
+      // trailing update: lane owns columns j0, j0+32; rows in batches of 4
+      const int j0 = k + 1 + lane, j1 = j0 + 32;
+      const double l0 = j0 < n ? col[j0] : 0.0;
+      const double l1 = j1 < n ? col[j1] : 0.0;
+      for (int i0 = k + 1; i0 < nrows; i0 += 4) {
+        double li[4], a0[4], a1[4];
+        bool p0v[4], p1v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+          const int jmax = i < n ? i : n - 1;  // last column stored in row i
+          p0v[q] = i < nrows && j0 <= jmax;
+          p1v[q] = i < nrows && j1 <= jmax;
+          const int o = prow(min(i, nrows - 1), n);
+          li[q] = col[min(i, nrows - 1)];
+          a0[q] = p0v[q] ? L[o + j0] : 0.0;
+          a1[q] = p1v[q] ? L[o + j1] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int o = prow(min(i0 + q, nrows - 1), n);
+          if (p0v[q]) L[o + j0] = fma(-li[q], l0, a0[q]);
+          if (p1v[q]) L[o + j1] = fma(-li[q], l1, a1[q]);
+        }
+      }
+      __syncwarp();
+    }
+    if (bad) {
+      if (lane == 0) a.status[t] = KRIGE_RETRY;
+      __syncwarp();
+      continue;
+    }
+    // y1 = row n, y2 = row n+1;  mu = (1 - y2.y1) / (y2.y2)
+    double s11 = 0.0, s12 = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double y1 = L[rowc + i], y2 = L[rowo + i];
+      s12 = fma(y2, y1, s12);
+      s11 = fma(y2, y2, s11);
+    }
+    s12 = warp_sum(s12);
+    s11 = warp_sum(s11);
+    s12 = __shfl_sync(0xffffffffu, s12, 0);
+    s11 = __shfl_sync(0xffffffffu, s11, 0);
+    const double mu = (1.0 - s12) / s11;
+    for (int i = lane; i < n; i += 32) xv[i] = fma(mu, L[rowo + i], L[rowc + i]);
+    __syncwarp();
+    // back substitution L' w = y (column walks of the packed rows)
+    for (int i = n - 1; i >= 0; --i) {
+      double acc = 0.0;
+      for (int j = i + 1 + lane; j < n; j += 32) acc = fma(L[prow(j, n) + i], xv[j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) xv[i] = (xv[i] - acc) / L[prow(i, n) + i];
+      __syncwarp();
+    }
+    double sz = 0.0, ss = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double w = xv[i];
+      sz = fma(w, nval[i], sz);   // Kriging.py:647
+      ss = fma(w, gvec[i], ss);   // Kriging.py:644
+    }
+    sz = warp_sum(sz);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      a.z[t] = sz;
+      a.sigma[t] = ss + mu;
+      a.status[t] = SKG_KRIGE_OK;
+    }
+    __syncwarp();
+  }
+}
+
 static int parse_grid(const double* grid, int dim, GridParams* g) {
   if (!grid) { set_error("grid NULL"); return SKG_E_BADARG; }
   g->ox = grid[0]; g->oy = grid[1]; g->oz = grid[2]; g->h = grid[3];
@@ -526,6 +793,28 @@ static void krige_layout(int max_points, int dim, int* cap, int* region, int* pe
   *cap = reg / 12;
   *region = reg;
   *per_warp = reg + (dim + 1) * max_points * 8 + 2 * (max_points + 1) * 8;
+}
+
+static void krige_chol_layout(int max_points, int dim, int* cap, int* region, int* per_warp) {
+  const int n = max_points;
+  int reg = (n * (n + 1) / 2 + 2 * n) * 8;
+  reg = std::max(reg, 1024 * 12);
+  reg = (reg + 15) & ~15;
+  *cap = reg / 12;
+  *region = reg;
+  *per_warp = reg + (dim + 3) * n * 8 + (n + 2) * 8;
+}
+
+// warps per CTA that maximise resident warps per SM for a given per-warp footprint
+static int best_wpb(int per_warp, int smem_budget) {
+  int best = 0, best_w = 1;
+  for (int w = 8; w >= 1; --w) {
+    if ((size_t)w * per_warp > (size_t)smem_budget) continue;
+    const int ctas = std::min(32, smem_budget / (w * per_warp + 1024));
+    const int resident = std::min(64, ctas * w);
+    if (resident > best) { best = resident; best_w = w; }
+  }
+  return best ? best_w : 0;
 }
 
 }  // namespace skg
@@ -610,22 +899,43 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
   a.radius = radius; a.min_points = min_points; a.max_points = max_points;
   a.z = z; a.sigma = sigma; a.status = status; a.t0 = target_begin; a.t1 = target_end;
   if (target_end == target_begin) return 0;
-  int per_warp = 0;
-  krige_layout(max_points, dim, &a.cap, &a.region_bytes, &per_warp);
-  const int smem_max = 220 * 1024;
-  int wpb = std::min(8, smem_max / per_warp);
-  if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
-  const size_t smem = (size_t)wpb * per_warp;
   cudaStream_t st = (cudaStream_t)stream;
-  auto kern = dim == 3 ? krige_kernel<3> : krige_kernel<2>;
-  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
-  occ = std::max(1, occ);
+  const int smem_budget = 226 * 1024;
   const int64_t ntarget = target_end - target_begin;
-  const int64_t grid_blocks = std::min<int64_t>((ntarget + wpb - 1) / wpb, (int64_t)sm_count() * occ);
-  kern<<<(unsigned)grid_blocks, wpb * 32, smem, st>>>(a);
-  SKG_CUDA(cudaGetLastError());
+  // pass 1: covariance-form Cholesky (fast path)
+  {
+    KrigeArgs c = a;
+    int per_warp = 0;
+    krige_chol_layout(max_points, dim, &c.cap, &c.region_bytes, &per_warp);
+    const int wpb = best_wpb(per_warp, smem_budget);
+    if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
+    const size_t smem = (size_t)wpb * per_warp;
+    auto kern = dim == 3 ? krige_chol_kernel<3> : krige_chol_kernel<2>;
+    SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    occ = std::max(1, occ);
+    const int64_t grid_blocks = std::min<int64_t>((ntarget + wpb - 1) / wpb, (int64_t)sm_count() * occ);
+    kern<<<(unsigned)grid_blocks, wpb * 32, smem, st>>>(c);
+    SKG_CUDA(cudaGetLastError());
+  }
+  // pass 2: partial-pivot LU of the original system for targets marked KRIGE_RETRY
+  {
+    int per_warp = 0;
+    krige_layout(max_points, dim, &a.cap, &a.region_bytes, &per_warp);
+    a.retry_only = 1;
+    const int wpb = best_wpb(per_warp, smem_budget);
+    if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
+    const size_t smem = (size_t)wpb * per_warp;
+    auto kern = dim == 3 ? krige_kernel<3> : krige_kernel<2>;
+    SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    occ = std::max(1, occ);
+    const int64_t grid_blocks = std::min<int64_t>((ntarget + wpb - 1) / wpb, (int64_t)sm_count() * occ);
+    kern<<<(unsigned)grid_blocks, wpb * 32, smem, st>>>(a);
+    SKG_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
