@@ -688,43 +688,74 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     __syncwarp();
 
     // ---- Cholesky, rows n and n+1 (rhs) carried along ---------------------
+    // Row-synchronous right-looking form: at step k the lanes own columns j0 = k+1+lane
+    // and j1 = j0+32 and sweep the rows together, so every access is a contiguous,
+    // conflict-free row segment and col[i] is a broadcast.  Row offsets advance by i+1.
     bool bad = false;
-    const int nrows = n + 2;
     for (int k = 0; k < n; ++k) {
-      const double akk = L[prow(k, n) + k];
+      const int ok = k * (k + 1) / 2;
+      const double akk = L[ok + k];
       if (!(akk > 0.0)) { bad = true; break; }
       const double rd = 1.0 / sqrt(akk);
-      for (int i = k + 1 + lane; i < nrows; i += 32) {
-        const int o = prow(i, n) + k;
-        const double l = L[o] * rd;
-        L[o] = l;
-        col[i] = l;
-      }
-      if (lane == 0) L[prow(k, n) + k] = akk * rd;
-      __syncwarp();
-      // trailing update: lane owns columns j0, j0+32; rows in batches of 4
-      const int j0 = k + 1 + lane, j1 = j0 + 32;
-      const double l0 = j0 < n ? col[j0] : 0.0;
-      const double l1 = j1 < n ? col[j1] : 0.0;
-      for (int i0 = k + 1; i0 < nrows; i0 += 4) {
-        double li[4], a0[4], a1[4];
-        bool p0v[4], p1v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = i0 + q;
-          const int jmax = i < n ? i : n - 1;  // last column stored in row i
-          p0v[q] = i < nrows && j0 <= jmax;
-          p1v[q] = i < nrows && j1 <= jmax;
-          const int o = prow(min(i, nrows - 1), n);
-          li[q] = col[min(i, nrows - 1)];
-          a0[q] = p0v[q] ? L[o + j0] : 0.0;
-          a1[q] = p1v[q] ? L[o + j1] : 0.0;
+      {  // scale column k (rows k+1 .. n-1, then the two rhs rows)
+        for (int i = k + 1 + lane; i < n; i += 32) {
+          const int o = i * (i + 1) / 2 + k;
+          const double l = L[o] * rd;
+          L[o] = l;
+          col[i] = l;
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int o = prow(min(i0 + q, nrows - 1), n);
-          if (p0v[q]) L[o + j0] = fma(-li[q], l0, a0[q]);
-          if (p1v[q]) L[o + j1] = fma(-li[q], l1, a1[q]);
+        if (lane < 2) {
+          const int o = (lane == 0 ? rowc : rowo) + k;
+          const double l = L[o] * rd;
+          L[o] = l;
+          col[n + lane] = l;
+        }
+        if (lane == 2) L[ok + k] = akk * rd;
+      }
+      __syncwarp();
+      const int j0 = k + 1 + lane, j1 = j0 + 32;
+      const bool h0 = j0 < n, h1 = j1 < n;
+      const double l0 = h0 ? col[j0] : 0.0;
+      const double l1 = h1 ? col[j1] : 0.0;
+      // columns k+1 .. k+32 : rows k+1 .. n-1
+      {
+        int o = (k + 1) * (k + 2) / 2;
+        int i = k + 1;
+        for (; i + 1 < n; i += 2) {
+          const int o2 = o + i + 1;
+          const double la = col[i], lb = col[i + 1];
+          const bool pa = j0 <= i, pb = j0 <= i + 1;
+          const double xa = pa ? L[o + j0] : 0.0;
+          const double xb = pb ? L[o2 + j0] : 0.0;
+          if (pa) L[o + j0] = fma(-la, l0, xa);
+          if (pb) L[o2 + j0] = fma(-lb, l0, xb);
+          o = o2 + i + 2;
+        }
+        if (i < n) {
+          if (j0 <= i) L[o + j0] = fma(-col[i], l0, L[o + j0]);
+        }
+      }
+      // columns k+33 .. : rows k+33 .. n-1
+      if (k + 33 < n) {
+        int i = k + 33;
+        int o = i * (i + 1) / 2;
+        for (; i < n; ++i) {
+          if (j1 <= i) L[o + j1] = fma(-col[i], l1, L[o + j1]);
+          o += i + 1;
+        }
+      }
+      // the two rhs rows
+      {
+        const double lc = col[n], lo = col[n + 1];
+        if (h0) {
+          const double xa = L[rowc + j0], xb = L[rowo + j0];
+          L[rowc + j0] = fma(-lc, l0, xa);
+          L[rowo + j0] = fma(-lo, l0, xb);
+        }
+        if (h1) {
+          const double xa = L[rowc + j1], xb = L[rowo + j1];
+          L[rowc + j1] = fma(-lc, l1, xa);
+          L[rowo + j1] = fma(-lo, l1, xb);
         }
       }
       __syncwarp();
