@@ -76,6 +76,7 @@ class Variogram:
         self._n_lags = None
         self.n_lags = n_lags
         self._maxlag = None
+        self._maxlag_within_range = False
         self.maxlag = maxlag
 
         self._estimator = None
@@ -211,17 +212,20 @@ class Variogram:
         """Variogram.py:1274-1295."""
         self._bins = None
         self._reset_pair_state()
+        self._maxlag_within_range = False
         if value is None:
             self._maxlag = None
         elif isinstance(value, str):
             if value == "median":
                 self._maxlag = self._distance_median()
+                self._maxlag_within_range = True
             elif value == "mean":
                 # np.mean sums the condensed vector pairwise in its storage order; the
                 # only way to get that exact value is to form the vector (as the reference)
                 self._maxlag = np.mean(self.distance)
         elif value < 1:
             self._maxlag = value * self._distance_max()
+            self._maxlag_within_range = value >= 0
         else:
             self._maxlag = value
 
@@ -240,10 +244,7 @@ class Variogram:
     def _distance_order_stats(self, rank_fn, masked=False, limit=None):
         dirp = self._dirp() if masked else None
         eng = self._X.engine(self._process_group)
-        vals, total, max_s = eng.sq_order_stats(rank_fn, dirp=dirp, limit=limit)
-        if max_s is not None:
-            self._X._cache.setdefault(("dmax", self._dir_key() if masked else None),
-                                      float(np.sqrt(np.float64(max_s))))
+        vals, total = eng.sq_order_stats(rank_fn, dirp=dirp, limit=limit)
         return {r: float(np.sqrt(np.float64(s))) for r, s in vals.items()}, total
 
     def _distance_median(self):
@@ -307,6 +308,10 @@ class Variogram:
         n, maxlag = self._n_lags, self._maxlag
         masked = self._dirp() is not None
         if self._bin_func == "even":
+            if maxlag is not None and not masked and self._maxlag_within_range:
+                # maxlag came from the distance distribution itself (median / ratio of the
+                # max): the clamp `maxlag > nanmax(d)` of binning.py:37 cannot trigger
+                return np.linspace(0, maxlag, n + 1)[1:], None
             dmax = self._distance_max(masked)
             if dmax is None:
                 raise ValueError("no point pair passes the directional mask")

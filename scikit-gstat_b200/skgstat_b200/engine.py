@@ -404,24 +404,99 @@ class PairEngine:
             b >>= 1
         return b
 
+    COARSE_CLASSES = 32
+
+    def hist_counts(self, thr: np.ndarray, dirp=None) -> np.ndarray:
+        """Exact pair counts per class of squared distance for bit-pattern thresholds
+        `thr` (skg_pair_hist with no estimator statistic: private counters, no atomics).
+        No values needed; all-reduced over the group."""
+        nl = int(thr.size)
+        cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
+        scratch = self._hist_scratch(nl)
+        vals = self.values if self.values is not None else self._buffer("zeros", self.n, torch.float64)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_hist(
+                _ptr(self.coords), _ptr(vals), self.n, self.dim, _hptr(dirp), _hptr(thr), nl, 0,
+                _ptr(cnt), None, None, _ptr(scratch), scratch.numel(), self.t0, self.t1,
+                self._stream())
+        _lib.check(rc, "skg_pair_hist")
+        self.launches += 2 if self.t1 > self.t0 else 0
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, _ = self._amb_keys(amb)
+            g = np.searchsorted(thr, s_bits, side="right")
+            extra = np.bincount(g[g < nl], minlength=nl).astype(np.int64)
+            cnt += to_device(extra, self.device)
+        D.allreduce_sum_(cnt, self.group)
+        return to_host(cnt).astype(np.int64)
+
     def sq_order_stats(self, rank_fn, dirp=None, limit: Optional[float] = None):
         """Exact order statistics of the squared distances s of all (mask-passing)
         pairs with fl(sqrt(s)) <= limit.  rank_fn(total) -> 0-based ranks.
-        Returns (dict rank -> s, total, max_s) where max_s is the largest s of all
-        mask-passing pairs (window ignored; None if there is no pair)."""
+        Returns (dict rank -> s, total).
+
+        Three sweeps, only the last two touch atomics and only for ~1/32 of the pairs per
+        wanted rank: (1) exact counts over COARSE_CLASSES classes linear in s with the
+        fused-pass kernel (private counters); (2) fine bucket histogram restricted to the
+        classes that hold a wanted rank; (3) gather of the target buckets."""
         from ._exact import sq_upper_inclusive_bits
         ub = self.sq_upper_bound()
         hi_bits = to_bits(ub) + 1
         if limit is not None:
             hi_bits = min(hi_bits, sq_upper_inclusive_bits(limit))
-        nb = self._buckets_for(self.n_pairs, 1)
-        mx = []
-        rh, rg = self._select_runner(_lib.KEY_SQDIST, None, dirp, nb, collect_max=mx)
-        vals, totals = exact_select(1, [0], [hi_bits], nb, lambda g, t: rank_fn(t), rh, rg)
-        # max over the first pass only (later passes see sub-windows but the max is global)
-        max_bits = mx[0] if mx else 0
-        max_s = from_bits(max_bits) if totals[0] > 0 or max_bits > 0 else None
-        return vals[0], totals[0], max_s
+        hi_val = from_bits(hi_bits)
+        C = self.COARSE_CLASSES
+        edges_s = [hi_val * (k + 1) / C for k in range(C - 1)] + [hi_val]
+        thr = np.array([to_bits(x) for x in edges_s], dtype=np.uint64)
+        thr = np.maximum.accumulate(thr)
+        thr[-1] = hi_bits
+        counts = self.hist_counts(thr, dirp)
+        total = int(counts.sum())
+        ranks = sorted(set(int(r) for r in rank_fn(total)))
+        for r in ranks:
+            if not (0 <= r < total):
+                raise ValueError("rank %d outside [0, %d)" % (r, total))
+        if not ranks:
+            return {}, total
+        cum = np.cumsum(counts)
+        cls = np.searchsorted(cum, np.asarray(ranks, dtype=np.int64), side="right")
+        wanted = sorted(set(int(c) for c in cls))
+        # window table: [lo_1, hi_1, lo_2, hi_2, ...]; class 2w+1 = inside window w
+        bounds, win_lo, win_hi, base = [], [], [], []
+        for c in wanted:
+            lo = int(thr[c - 1]) if c > 0 else 0
+            hi = int(thr[c])
+            bounds += [lo, hi]
+            win_lo.append(lo)
+            win_hi.append(hi)
+            base.append(int(cum[c - 1]) if c > 0 else 0)
+        wthr = np.array(bounds, dtype=np.uint64)
+        nseg = len(bounds)
+        lo_bits = [0] * nseg
+        hi_bits_l = [0] * nseg
+        for w in range(len(wanted)):
+            lo_bits[2 * w + 1] = win_lo[w]
+            hi_bits_l[2 * w + 1] = win_hi[w]
+        seg_of_class = {c: 2 * w + 1 for w, c in enumerate(wanted)}
+        seg_ranks = {}
+        for r, c in zip(ranks, cls):
+            seg_ranks.setdefault(seg_of_class[int(c)], []).append(r - base[wanted.index(int(c))])
+        nb = 1 << 10
+        while nb < (1 << 16) and nb * 256 < int(counts[wanted].max()):
+            nb <<= 1
+        while nseg * nb > (1 << 22) and nb > 256:
+            nb >>= 1
+        rh, rg = self._select_runner(_lib.KEY_SQDIST, wthr, dirp, nb)
+        vals, totals = exact_select(nseg, lo_bits, hi_bits_l, nb,
+                                    lambda g, t: seg_ranks.get(g, []), rh, rg)
+        out = {}
+        for r, c in zip(ranks, cls):
+            w = wanted.index(int(c))
+            seg = 2 * w + 1
+            if totals[seg] != int(counts[int(c)]):
+                raise RuntimeError("coarse/fine count mismatch in class %d" % int(c))
+            out[r] = vals[seg][r - base[w]]
+        return out, total
 
     def sq_max(self, dirp=None):
         """Largest squared distance among the (mask-passing) pairs (None if no pair
