@@ -116,18 +116,20 @@ def morton_order(c: np.ndarray) -> np.ndarray:
     the same or adjacent lag classes: the lag-table reads broadcast, the per-lag
     accumulator traffic is skipped for whole warps outside maxlag.  Results do not
     depend on the order (counts exactly, sums to rounding)."""
-    n, dim = c.shape
-    lo = c.min(axis=0)
-    ext = c.max(axis=0) - lo
-    ext[ext <= 0] = 1.0
+    ct = np.ascontiguousarray(c.T)  # contiguous per-dimension rows: fast reductions
+    dim, n = ct.shape
     bits = 21 if dim == 3 else 31
-    with np.errstate(invalid="ignore"):
-        q = ((c - lo) * ((2 ** bits - 1) / ext)).astype(np.int64)  # NaN -> arbitrary cell
-    q = np.clip(q, 0, 2 ** bits - 1).astype(np.uint64)
     u = np.uint64
     key = np.zeros(n, dtype=np.uint64)
     for k in range(dim):
-        v = q[:, k].copy()
+        row = ct[k]
+        lo = np.nanmin(row) if n else 0.0
+        ext = (np.nanmax(row) - lo) if n else 1.0
+        if not (ext > 0):
+            ext = 1.0
+        with np.errstate(invalid="ignore"):
+            q = ((row - lo) * ((2 ** bits - 1) / ext)).astype(np.int64)  # NaN -> arbitrary cell
+        v = np.clip(q, 0, 2 ** bits - 1).astype(np.uint64)
         if dim == 2:  # spread 32 bits to even positions
             v = (v | (v << u(16))) & u(0x0000FFFF0000FFFF)
             v = (v | (v << u(8))) & u(0x00FF00FF00FF00FF)
@@ -163,10 +165,11 @@ class PairEngine:
         self.perm = morton_order(c) if self.n > 64 else np.arange(self.n)
         self._orig_coords = c
         self._host_coords = np.ascontiguousarray(c[self.perm])
+        self._host_coords_t = np.ascontiguousarray(self._host_coords.T)
         self._coords_unsorted = None
         self._values_unsorted = None
         with torch.cuda.device(self.device):
-            self.coords = to_device(self._host_coords.T, self.device)
+            self.coords = to_device(self._host_coords_t, self.device)
         self.values = None
         self._host_values = None
         self._vmin = self._vmax = 0.0
@@ -194,9 +197,9 @@ class PairEngine:
         v = np.ascontiguousarray(v[self.perm])
         self.values = to_device(v, self.device)
         self._host_values = v
-        finite = v[np.isfinite(v)]
-        self._vmin = float(finite.min()) if finite.size else 0.0
-        self._vmax = float(finite.max()) if finite.size else 0.0
+        with np.errstate(invalid="ignore"):
+            self._vmin = float(np.nanmin(v)) if v.size else 0.0
+            self._vmax = float(np.nanmax(v)) if v.size else 0.0
 
     def _buffer(self, name, numel, dtype):
         """Persistent device scratch (avoids allocator round trips on every call)."""
@@ -217,7 +220,8 @@ class PairEngine:
 
     def sq_upper_bound(self) -> float:
         """A value >= every squared pair distance (bounding-box diagonal, padded)."""
-        ext = self._host_coords.max(axis=0) - self._host_coords.min(axis=0)
+        ct = self._host_coords_t
+        ext = np.array([np.nanmax(r) - np.nanmin(r) for r in ct]) if self.n else np.zeros(self.dim)
         ub = float(np.sum(ext * ext)) * (1.0 + 1e-12)
         return ub if ub > 0.0 else 1.0
 
