@@ -687,75 +687,70 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     }
     __syncwarp();
 
-    // ---- Cholesky, rows n and n+1 (rhs) carried along ---------------------
-    // Row-synchronous right-looking form: at step k the lanes own columns j0 = k+1+lane
-    // and j1 = j0+32 and sweep the rows together, so every access is a contiguous,
-    // conflict-free row segment and col[i] is a broadcast.  Row offsets advance by i+1.
+    // ---- blocked Cholesky, rows n and n+1 (rhs) carried along --------------
+    // Right-looking with 8-column panels.  The panel is factored with plain fp64 FMAs
+    // (lanes over rows); the trailing update  A22 -= P P'  runs on the FP64 tensor cores
+    // (mma.sync m8n8k4, 8x8 output tiles, two k=4 steps per panel), which replaces ~30
+    // warp-FMAs per tile by two instructions.
     bool bad = false;
-    for (int k = 0; k < n; ++k) {
-      const int ok = k * (k + 1) / 2;
-      const double akk = L[ok + k];
-      if (!(akk > 0.0)) { bad = true; break; }
-      const double rd = 1.0 / sqrt(akk);
-      {  // scale column k (rows k+1 .. n-1, then the two rhs rows)
-        for (int i = k + 1 + lane; i < n; i += 32) {
-          const int o = i * (i + 1) / 2 + k;
-          const double l = L[o] * rd;
-          L[o] = l;
-          col[i] = l;
+    const int R = n + 2;                 // rows incl. the two rhs rows
+    const int ncb = (n + 7) >> 3;        // column blocks
+    const int nrb = (R + 7) >> 3;        // row blocks
+    const int grp = lane >> 2, tig = lane & 3;
+    for (int bk = 0; bk < ncb && !bad; ++bk) {
+      const int kb = bk << 3;
+      const int ke = min(kb + 8, n);
+      for (int k = kb; k < ke; ++k) {
+        const int ok = k * (k + 1) / 2;
+        const double akk = L[ok + k];
+        if (!(akk > 0.0)) { bad = true; break; }
+        const double rd = 1.0 / sqrt(akk);
+        for (int i = k + 1 + lane; i < R; i += 32) {
+          const int o = prow(i, n) + k;
+          L[o] *= rd;
         }
-        if (lane < 2) {
-          const int o = (lane == 0 ? rowc : rowo) + k;
-          const double l = L[o] * rd;
-          L[o] = l;
-          col[n + lane] = l;
+        if (lane == 0) L[ok + k] = akk * rd;
+        __syncwarp();
+        // remaining panel columns c in (k, ke): L[i][c] -= L[i][k] * L[c][k]
+        if (k + 1 < ke) {
+          for (int i = k + 1 + lane; i < R; i += 32) {
+            const int o = prow(i, n);
+            const double li = L[o + k];
+            const int cmax = i < n ? min(i, ke - 1) : ke - 1;
+            for (int c = k + 1; c <= cmax; ++c)
+              L[o + c] = fma(-li, L[c * (c + 1) / 2 + k], L[o + c]);
+          }
         }
-        if (lane == 2) L[ok + k] = akk * rd;
+        __syncwarp();
       }
-      __syncwarp();
-      const int j0 = k + 1 + lane, j1 = j0 + 32;
-      const bool h0 = j0 < n, h1 = j1 < n;
-      const double l0 = h0 ? col[j0] : 0.0;
-      const double l1 = h1 ? col[j1] : 0.0;
-      // columns k+1 .. k+32 : rows k+1 .. n-1
-      {
-        int o = (k + 1) * (k + 2) / 2;
-        int i = k + 1;
-        for (; i + 1 < n; i += 2) {
-          const int o2 = o + i + 1;
-          const double la = col[i], lb = col[i + 1];
-          const bool pa = j0 <= i, pb = j0 <= i + 1;
-          const double xa = pa ? L[o + j0] : 0.0;
-          const double xb = pb ? L[o2 + j0] : 0.0;
-          if (pa) L[o + j0] = fma(-la, l0, xa);
-          if (pb) L[o2 + j0] = fma(-lb, l0, xb);
-          o = o2 + i + 2;
-        }
-        if (i < n) {
-          if (j0 <= i) L[o + j0] = fma(-col[i], l0, L[o + j0]);
-        }
-      }
-      // columns k+33 .. : rows k+33 .. n-1
-      if (k + 33 < n) {
-        int i = k + 33;
-        int o = i * (i + 1) / 2;
-        for (; i < n; ++i) {
-          if (j1 <= i) L[o + j1] = fma(-col[i], l1, L[o + j1]);
-          o += i + 1;
-        }
-      }
-      // the two rhs rows
-      {
-        const double lc = col[n], lo = col[n + 1];
-        if (h0) {
-          const double xa = L[rowc + j0], xb = L[rowo + j0];
-          L[rowc + j0] = fma(-lc, l0, xa);
-          L[rowo + j0] = fma(-lo, l0, xb);
-        }
-        if (h1) {
-          const double xa = L[rowc + j1], xb = L[rowo + j1];
-          L[rowc + j1] = fma(-lc, l1, xa);
-          L[rowo + j1] = fma(-lo, l1, xb);
+      if (bad) break;
+      // trailing update on the tensor cores: tiles (I, J), J > bk, I >= J
+      for (int I = bk + 1; I < nrb; ++I) {
+        const int r = (I << 3) + grp;           // this lane's row of the A and C fragments
+        const bool rv = r < R;
+        const int orow = prow(rv ? r : 0, n);
+        double a0 = 0.0, a1 = 0.0;              // -P[r][kb + tig], -P[r][kb + 4 + tig]
+        if (rv && kb + tig < ke) a0 = -L[orow + kb + tig];
+        if (rv && kb + 4 + tig < ke) a1 = -L[orow + kb + 4 + tig];
+        const int jhi = min(I, ncb - 1);
+        for (int J = bk + 1; J <= jhi; ++J) {
+          const int rj = (J << 3) + grp;        // row of P feeding column rj of the tile
+          const bool jv = rj < n;
+          const int oj = prow(jv ? rj : 0, n);
+          double b0 = 0.0, b1 = 0.0;
+          if (jv && kb + tig < ke) b0 = L[oj + kb + tig];
+          if (jv && kb + 4 + tig < ke) b1 = L[oj + kb + 4 + tig];
+          const int c0 = (J << 3) + 2 * tig, c1 = c0 + 1;
+          const bool v0 = rv && c0 < n && (c0 <= r || r >= n);
+          const bool v1 = rv && c1 < n && (c1 <= r || r >= n);
+          double d0 = v0 ? L[orow + c0] : 0.0;
+          double d1 = v1 ? L[orow + c1] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(d0), "+d"(d1) : "d"(a0), "d"(b0));
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(d0), "+d"(d1) : "d"(a1), "d"(b1));
+          if (v0) L[orow + c0] = d0;
+          if (v1) L[orow + c1] = d1;
         }
       }
       __syncwarp();
