@@ -663,7 +663,7 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
       for (int q = 0; q < 2; ++q) {
         const int p = min(p0 + 32 * q, npairs - 1);
         // p -> (j, i), i < j: packed strictly-lower index p = j(j-1)/2 + i
-        int j = (int)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+        int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);  // exact after the fix-ups
         while (j * (j - 1) / 2 > p) --j;
         while ((j + 1) * j / 2 <= p) ++j;
         pj[q] = j;
@@ -772,16 +772,21 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     s12 = __shfl_sync(0xffffffffu, s12, 0);
     s11 = __shfl_sync(0xffffffffu, s11, 0);
     const double mu = (1.0 - s12) / s11;
-    for (int i = lane; i < n; i += 32) xv[i] = fma(mu, L[rowo + i], L[rowc + i]);
-    __syncwarp();
-    // back substitution L' w = y (column walks of the packed rows)
+    // back substitution L' w = y1 + mu y2 in axpy form: y lives in registers (lane owns
+    // entries lane and lane+32), row i of L is read contiguously, no reductions
+    double yA = lane < n ? fma(mu, L[rowo + lane], L[rowc + lane]) : 0.0;
+    double yB = lane + 32 < n ? fma(mu, L[rowo + lane + 32], L[rowc + lane + 32]) : 0.0;
     for (int i = n - 1; i >= 0; --i) {
-      double acc = 0.0;
-      for (int j = i + 1 + lane; j < n; j += 32) acc = fma(L[prow(j, n) + i], xv[j], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) xv[i] = (xv[i] - acc) / L[prow(i, n) + i];
-      __syncwarp();
+      const int oi = i * (i + 1) / 2;
+      const double yi = __shfl_sync(0xffffffffu, i < 32 ? yA : yB, i & 31);
+      const double wi = yi / L[oi + i];
+      if (lane == (i & 31)) { if (i < 32) yA = wi; else yB = wi; }
+      if (lane < i) yA = fma(-L[oi + lane], wi, yA);
+      if (lane + 32 < i) yB = fma(-L[oi + lane + 32], wi, yB);
     }
+    if (lane < n) xv[lane] = yA;
+    if (lane + 32 < n) xv[lane + 32] = yB;
+    __syncwarp();
     double sz = 0.0, ss = 0.0;
     for (int i = lane; i < n; i += 32) {
       const double w = xv[i];
