@@ -383,88 +383,143 @@ pair_hist_reduce_kernel(const HistPartial* __restrict__ partial, int nblocks, in
 
 // ------------------------------------------------- K1/K3: select passes ---
 
-template <bool DIR, bool SEG, int KEY, bool GATHER>
-struct SelectOp {
-  const uint64_t* sThr;
-  const uint8_t* sLut;
-  int key0, shift, ncell, emax, nb;
-  const DirParams* dp;
-  const SegTable* seg;
-  long long nbuckets;
-  unsigned long long* hist;
-  unsigned long long local_max;
-  // gather
-  const uint32_t* bitmap;
-  double* cand_key;
-  uint32_t* cand_slot;
-  unsigned long long* cand_count;
-  long long capacity;
-
-  __device__ __forceinline__ void pair(double s, double dx, double dy, double zi, double zj, int64_t, int64_t) {
-    const uint64_t sb = (uint64_t)__double_as_longlong(s);
-    if (sb > INF_BITS) return;  // NaN: padded / i>=j / NaN coordinate
-    int g = 0;
-    if (SEG) {
-      g = find_bin(sb, sThr, sLut, key0, shift, ncell, emax);
-      if (g >= nb) return;
-    }
-    if (DIR) {
-      if (!dir_mask(dx, dy, s, *dp)) return;
-    }
-    const double key = (KEY == SKG_KEY_SQDIST) ? s : fabs(zi - zj);
-    const uint64_t kb = (uint64_t)__double_as_longlong(key);
-    if (kb > INF_BITS) return;
-    if (!SEG && !GATHER) local_max = kb > local_max ? kb : local_max;
-    if (kb < seg->lo_bits[g] || kb >= seg->hi_bits[g]) return;
-    const double lo = __longlong_as_double((long long)seg->lo_bits[g]);
-    long long b = __double2ll_rz(__dmul_rn(__dsub_rn(key, lo), seg->scale[g]));
-    b = b < nbuckets - 1 ? b : nbuckets - 1;
-    const long long slot = (long long)g * nbuckets + b;
-    if (!GATHER) {
-      atomicAdd(&hist[slot], 1ull);
-    } else {
-      if ((bitmap[slot >> 5] >> (slot & 31)) & 1u) {
-        const unsigned long long pos = atomicAdd(cand_count, 1ull);
-        if ((long long)pos < capacity) {
-          cand_key[pos] = key;
-          cand_slot[pos] = (uint32_t)slot;
-        }
-      }
-    }
-  }
-};
-
-template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER>
-__global__ void __launch_bounds__(BLOCK)
+// Same sweep structure as the fused kernel (64 threads x 4 "i" points, static tables,
+// j-chunk work items, software-pipelined front end).  Histogram pass: one u64 atomicAdd
+// (L2) per key INSIDE the segment's window - the host keeps the windows narrow (the class
+// that holds a wanted rank), so most pairs only pay the front end.  Gather pass: bitmap
+// test and append.  The per-thread running maximum of the keys feeds atomicMax once.
+template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER, int EMAX>
+__global__ void __launch_bounds__(HB)
 pair_select_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                    const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
                    const __grid_constant__ SegTable seg_tab, long long nbuckets,
                    unsigned long long* __restrict__ hist, unsigned long long* __restrict__ max_bits,
                    const uint32_t* __restrict__ bitmap, double* __restrict__ cand_key,
                    uint32_t* __restrict__ cand_slot, unsigned long long* __restrict__ cand_count,
-                   long long capacity, int64_t t0, int64_t t1) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<DIM>& sm = *reinterpret_cast<TileSmem<DIM>*>(smem_raw);
-  uint64_t* sThr = reinterpret_cast<uint64_t*>(smem_raw + sizeof(TileSmem<DIM>));
-  SegTable* sSeg = reinterpret_cast<SegTable*>(sThr + THR_MAX);
-  uint8_t* sLut = reinterpret_cast<uint8_t*>(sSeg + 1);
-  load_tables(tab, sThr, sLut);
-  const int nseg = SEG ? tab.nb : 1;
-  for (int k = threadIdx.x; k < nseg; k += BLOCK) {
-    sSeg->lo_bits[k] = seg_tab.lo_bits[k];
-    sSeg->hi_bits[k] = seg_tab.hi_bits[k];
-    sSeg->scale[k] = seg_tab.scale[k];
+                   long long capacity, int64_t t0, int64_t t1, int js) {
+  __shared__ double2 sXY[TILE + 2];
+  __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
+  __shared__ double sZ[TILE + 2];
+  __shared__ uint64_t sThr[THR_MAX];
+  __shared__ uint8_t sLut[LUT_MAX];
+  __shared__ SegTable sSeg;
+  const int tid = threadIdx.x;
+  const int nb = SEG ? tab.nb : 1;
+  const double qnan = __longlong_as_double(NAN_BITS);
+  for (int k = tid; k < THR_MAX; k += HB) sThr[k] = tab.thr[k];
+  for (int k = tid; k < tab.ncell; k += HB) sLut[k] = tab.lut[k];
+  for (int k = tid; k < nb; k += HB) {
+    sSeg.lo_bits[k] = seg_tab.lo_bits[k];
+    sSeg.hi_bits[k] = seg_tab.hi_bits[k];
+    sSeg.scale[k] = seg_tab.scale[k];
   }
   __syncthreads();
-  SelectOp<DIR, SEG, KEY, GATHER> op;
-  op.sThr = sThr; op.sLut = sLut;
-  op.key0 = tab.key0; op.shift = tab.shift; op.ncell = tab.ncell; op.emax = tab.emax; op.nb = tab.nb;
-  op.dp = &dp; op.seg = sSeg; op.nbuckets = nbuckets; op.hist = hist; op.local_max = 0ull;
-  op.bitmap = bitmap; op.cand_key = cand_key; op.cand_slot = cand_slot;
-  op.cand_count = cand_count; op.capacity = capacity;
-  sweep_tiles<DIM>(coords, values, n, t0, t1, sm, op);
+  const int shift = tab.shift, klo = tab.key0, khi = tab.key0 + tab.ncell - 1, emax = tab.emax;
+  const uint8_t* lutb = sLut - klo;
+  const int64_t nt = (n + TILE - 1) / TILE;
+  const double* __restrict__ X = coords;
+  const double* __restrict__ Y = coords + n;
+  const double* __restrict__ W = coords + 2 * n;
+  unsigned long long local_max = 0ull;
+  const int jchunk = TILE / js;
+
+  for (int64_t w = t0 * js + blockIdx.x; w < t1 * js; w += gridDim.x) {
+    const int64_t t = w / js;
+    const int jbeg = (int)(w - t * js) * jchunk;
+    int I, J;
+    tile_decode(t, nt, I, J);
+    double xi[HR], yi[HR], wi[HR], zi[HR];
+#pragma unroll
+    for (int r = 0; r < HR; ++r) {
+      const int64_t i = (int64_t)I * TILE + r * HB + tid;
+      const bool v = i < n;
+      xi[r] = v ? X[i] : qnan;
+      yi[r] = v ? Y[i] : qnan;
+      wi[r] = (DIM == 3) ? (v ? W[i] : qnan) : 0.0;
+      zi[r] = (v && values) ? values[i] : 0.0;
+    }
+    const int64_t jn = n - ((int64_t)J * TILE + jbeg);
+    const int jcount = jn < jchunk ? (jn > 0 ? (int)jn : 0) : jchunk;
+    __syncthreads();
+    for (int k = tid; k < jcount + 2; k += HB) {
+      const int64_t j = (int64_t)J * TILE + jbeg + k;
+      const bool v = k < jcount;
+      sXY[k] = make_double2(v ? X[j] : qnan, v ? Y[j] : qnan);
+      if (DIM == 3) sW[k] = v ? W[j] : qnan;
+      sZ[k] = (v && values) ? values[j] : 0.0;
+    }
+    __syncthreads();
+    if (jcount == 0) continue;
+
+    auto body = [&](auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
+      auto front = [&](int jj, int (&g)[HR], double (&key)[HR]) {
+        const double2 pj = sXY[jj];
+        const double zj = sZ[jj];
+        const double wj = (DIM == 3) ? sW[jj] : 0.0;
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          const double dx = xi[r] - pj.x;
+          const double dy = yi[r] - pj.y;
+          double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (DIM == 3) {
+            const double dw = wi[r] - wj;
+            s = __dadd_rn(s, __dmul_rn(dw, dw));
+          }
+          const uint64_t sb = (uint64_t)__double_as_longlong(s);
+          int gg;
+          if (SEG) gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
+          else gg = sb <= INF_BITS ? 0 : nb;  // NaN: padded point or NaN coordinate
+          if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
+          if (DIR) {
+            if (gg < nb && !dir_mask(dx, dy, s, dp)) gg = nb;
+          }
+          g[r] = gg;
+          key[r] = (KEY == SKG_KEY_SQDIST) ? s : fabs(zi[r] - zj);
+        }
+      };
+      auto accumulate = [&](const int (&g)[HR], const double (&key)[HR]) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          if (g[r] >= nb) continue;
+          const uint64_t kb = (uint64_t)__double_as_longlong(key[r]);
+          if (kb > INF_BITS) continue;  // NaN value
+          if (!SEG && !GATHER) local_max = kb > local_max ? kb : local_max;
+          if (kb < sSeg.lo_bits[g[r]] || kb >= sSeg.hi_bits[g[r]]) continue;
+          const double lo = __longlong_as_double((long long)sSeg.lo_bits[g[r]]);
+          long long bk = __double2ll_rz(__dmul_rn(__dsub_rn(key[r], lo), sSeg.scale[g[r]]));
+          bk = bk < nbuckets - 1 ? bk : nbuckets - 1;
+          const long long slot = (long long)g[r] * nbuckets + bk;
+          if (!GATHER) {
+            atomicAdd(&hist[slot], 1ull);
+          } else if ((bitmap[slot >> 5] >> (slot & 31)) & 1u) {
+            const unsigned long long pos = atomicAdd(cand_count, 1ull);
+            if ((long long)pos < capacity) {
+              cand_key[pos] = key[r];
+              cand_slot[pos] = (uint32_t)slot;
+            }
+          }
+        }
+      };
+      int gA[HR], gB[HR];
+      double kA[HR], kB[HR];
+      front(0, gA, kA);
+      int jj = 1;
+      for (; jj + 1 <= jcount; jj += 2) {
+        front(jj, gB, kB);
+        accumulate(gA, kA);
+        front(jj + 1, gA, kA);
+        accumulate(gB, kB);
+      }
+      if (jj <= jcount) {
+        front(jj, gB, kB);
+        accumulate(gA, kA);
+      }
+    };
+    if (I == J) body(std::true_type{}); else body(std::false_type{});
+  }
   if (!SEG && !GATHER && max_bits) {
-    unsigned long long m = op.local_max;
+    unsigned long long m = local_max;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       unsigned long long other = __shfl_down_sync(0xffffffffu, m, o);
@@ -652,6 +707,27 @@ static int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0,
 
 constexpr int MAX_GRID_PER_SM = 16;
 
+// (CTAs per SM, j-split) keeping the static round-robin balanced; shared by all sweeps
+static void choose_grid(int64_t tiles, int occ, int64_t* grid_out, int* js_out) {
+  const int sms = sm_count();
+  double best = -1.0;
+  int64_t grid = 1;
+  int js = 1;
+  for (int k = occ; k >= std::max(1, occ - 1); --k) {
+    for (int cand = 1; cand <= 16; cand *= 2) {
+      const int64_t items = tiles * cand;
+      const int64_t g = std::min<int64_t>((int64_t)sms * k, items);
+      const int64_t rounds = (items + g - 1) / g;
+      double eff = (double)items / ((double)g * (double)rounds);
+      eff *= (g >= (int64_t)sms * k) ? (0.92 + 0.08 * k / occ) : (double)g / ((double)sms * occ);
+      eff *= 1.0 - 0.012 * std::log2((double)cand);  // per-item staging overhead
+      if (eff > best) { best = eff; grid = g; js = cand; }
+    }
+  }
+  *grid_out = grid;
+  *js_out = js;
+}
+
 static size_t hist_smem_bytes(int nb, int stats, bool priv) {
   const size_t S = priv ? HB : 1;
   return (size_t)nb * S * (stats == 3 ? 32 : 16);
@@ -677,23 +753,9 @@ static int launch_hist(const HistLaunch& L) {
   int occ = cached_occ;
   if (occ < 1) { set_error("pair_hist kernel does not fit (smem=%zu)", L.smem); return SKG_E_UNSUPPORTED; }
   occ = std::min(occ, MAX_GRID_PER_SM);
-  // pick (CTAs per SM, j-split) that keeps the static round-robin balanced
-  const int64_t tiles = L.t1 - L.t0;
-  const int sms = sm_count();
-  double best = -1.0;
   int64_t grid = 1;
   int js = 1;
-  for (int k = occ; k >= std::max(1, occ - 1); --k) {
-    for (int cand = 1; cand <= 16; cand *= 2) {
-      const int64_t items = tiles * cand;
-      const int64_t g = std::min<int64_t>((int64_t)sms * k, items);
-      const int64_t rounds = (items + g - 1) / g;
-      double eff = (double)items / ((double)g * (double)rounds);
-      eff *= (g >= (int64_t)sms * k) ? (0.92 + 0.08 * k / occ) : (double)g / ((double)sms * occ);
-      eff *= 1.0 - 0.012 * std::log2((double)cand);  // per-item staging overhead
-      if (eff > best) { best = eff; grid = g; js = cand; }
-    }
-  }
+  choose_grid(L.t1 - L.t0, occ, &grid, &js);
   grid = std::min<int64_t>(grid, L.max_blocks);
   *L.nblocks_out = (int)grid;
   kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial,
@@ -731,18 +793,20 @@ static int launch_select(const double* coords, const double* values, int64_t n, 
                          uint64_t* hist, uint64_t* max_bits, const uint32_t* bitmap,
                          double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
                          int64_t capacity, int64_t t0, int64_t t1, cudaStream_t st) {
-  auto kern = pair_select_kernel<DIM, DIR, SEG, KEY, GATHER>;
-  const size_t smem = sizeof(TileSmem<DIM>) + THR_MAX * 8 + sizeof(SegTable) + LUT_MAX;
-  SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool e1 = tab.emax <= 1;
+  auto kern = e1 ? pair_select_kernel<DIM, DIR, SEG, KEY, GATHER, 1>
+                 : pair_select_kernel<DIM, DIR, SEG, KEY, GATHER, 0>;
   int occ = 0;
-  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+  SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HB, 0));
   occ = std::max(1, std::min(occ, MAX_GRID_PER_SM));
-  const int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, t1 - t0);
-  kern<<<(unsigned)grid, BLOCK, smem, st>>>(
+  int64_t grid = 1;
+  int js = 1;
+  choose_grid(t1 - t0, occ, &grid, &js);
+  kern<<<(unsigned)grid, HB, 0, st>>>(
       coords, values, n, tab, dp, seg_tab, (long long)nbuckets,
       reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(max_bits),
       bitmap, cand_key, cand_slot, reinterpret_cast<unsigned long long*>(cand_count),
-      (long long)capacity, t0, t1);
+      (long long)capacity, t0, t1, js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
