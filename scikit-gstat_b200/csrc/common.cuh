@@ -110,12 +110,19 @@ __device__ __forceinline__ bool dir_fast(double dx, double dy, const DirParams& 
   return ok;
 }
 
-__device__ __forceinline__ bool dir_mask(double dx, double dy, double s, const DirParams& p) {
+// LITERAL = false: guard-band pairs fail (policy 1, resolved by the caller) - no
+// transcendental code is even compiled into the sweep; LITERAL = true: policy 0.
+template <bool LITERAL>
+__device__ __forceinline__ bool dir_mask_t(double dx, double dy, double s, const DirParams& p) {
   if (!(s > 0.0)) return false;  // coincident points: 0/0 -> NaN angle -> every test false (:405)
   bool amb;
   bool ok = dir_fast(dx, dy, p, &amb);
-  if (amb) ok = p.amb_exclude ? false : dir_literal(dx, dy, s, p);
+  if (amb) ok = LITERAL ? dir_literal(dx, dy, s, p) : false;
   return ok;
+}
+
+__device__ __forceinline__ bool dir_mask(double dx, double dy, double s, const DirParams& p) {
+  return p.amb_exclude ? dir_mask_t<false>(dx, dy, s, p) : dir_mask_t<true>(dx, dy, s, p);
 }
 
 // tile index -> (I, J), I <= J, row-major over the upper triangle of nt x nt.

@@ -196,7 +196,7 @@ __device__ __forceinline__ int lag_of(uint64_t sb, const uint64_t* sThr, const u
 // PRIV: private per-thread records + software-pipelined loop (front end of pair set
 // jj+1 is issued before the read-modify-writes of pair set jj).
 // !PRIV (n_lags too large for private records): one shared record per lag + atomics.
-template <int DIM, bool DIR, int STATS, int EMAX, bool PRIV>
+template <int DIM, int DIR, int STATS, int EMAX, bool PRIV>
 __global__ void __launch_bounds__(HB)
 pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                  const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
@@ -281,7 +281,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
           int gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
           if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
           if (DIR) {
-            if (gg < nb && !dir_mask(dx, dy, s, dp)) gg = nb;
+            if (gg < nb && !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nb;
           }
           g[r] = gg;
           dz[r] = zi[r] - zj;
@@ -388,7 +388,7 @@ pair_hist_reduce_kernel(const HistPartial* __restrict__ partial, int nblocks, in
 // (L2) per key INSIDE the segment's window - the host keeps the windows narrow (the class
 // that holds a wanted rank), so most pairs only pay the front end.  Gather pass: bitmap
 // test and append.  The per-thread running maximum of the keys feeds atomicMax once.
-template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER, int EMAX>
+template <int DIM, int DIR, bool SEG, int KEY, bool GATHER, int EMAX>
 __global__ void __launch_bounds__(HB)
 pair_select_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                    const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
@@ -472,7 +472,7 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
           else gg = sb <= INF_BITS ? 0 : nb;  // NaN: padded point or NaN coordinate
           if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
           if (DIR) {
-            if (gg < nb && !dir_mask(dx, dy, s, dp)) gg = nb;
+            if (gg < nb && !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nb;
           }
           g[r] = gg;
           key[r] = (KEY == SKG_KEY_SQDIST) ? s : fabs(zi[r] - zj);
@@ -740,7 +740,7 @@ struct HistLaunch {
   int max_blocks; int64_t t0, t1; size_t smem; cudaStream_t st; int* nblocks_out;
 };
 
-template <int DIM, bool DIR, int STATS, int EMAX, bool PRIV>
+template <int DIM, int DIR, int STATS, int EMAX, bool PRIV>
 static int launch_hist(const HistLaunch& L) {
   auto kern = pair_hist_kernel<DIM, DIR, STATS, EMAX, PRIV>;
   static thread_local size_t cached_smem = (size_t)-1;
@@ -764,7 +764,7 @@ static int launch_hist(const HistLaunch& L) {
   return 0;
 }
 
-template <int DIM, bool DIR, int EMAX, bool PRIV>
+template <int DIM, int DIR, int EMAX, bool PRIV>
 static int dispatch_hist_stats(int stats, const HistLaunch& L) {
   switch (stats) {
     case 0: return launch_hist<DIM, DIR, 0, EMAX, PRIV>(L);
@@ -775,19 +775,20 @@ static int dispatch_hist_stats(int stats, const HistLaunch& L) {
 }
 
 template <int EMAX, bool PRIV>
-static int dispatch_hist_dim(int dim, bool dir, int stats, const HistLaunch& L) {
-  if (dim == 3) return dispatch_hist_stats<3, false, EMAX, PRIV>(stats, L);
-  if (dir) return dispatch_hist_stats<2, true, EMAX, PRIV>(stats, L);
-  return dispatch_hist_stats<2, false, EMAX, PRIV>(stats, L);
+static int dispatch_hist_dim(int dim, int dir, int stats, const HistLaunch& L) {
+  if (dim == 3) return dispatch_hist_stats<3, 0, EMAX, PRIV>(stats, L);
+  if (dir == 1) return dispatch_hist_stats<2, 1, EMAX, PRIV>(stats, L);
+  if (dir == 2) return dispatch_hist_stats<2, 2, EMAX, PRIV>(stats, L);
+  return dispatch_hist_stats<2, 0, EMAX, PRIV>(stats, L);
 }
 
-static int dispatch_hist(bool priv, int emax, int dim, bool dir, int stats, const HistLaunch& L) {
+static int dispatch_hist(bool priv, int emax, int dim, int dir, int stats, const HistLaunch& L) {
   if (!priv) return dispatch_hist_dim<0, false>(dim, dir, stats, L);
   if (emax <= 1) return dispatch_hist_dim<1, true>(dim, dir, stats, L);
   return dispatch_hist_dim<0, true>(dim, dir, stats, L);
 }
 
-template <int DIM, bool DIR, bool SEG, int KEY, bool GATHER>
+template <int DIM, int DIR, bool SEG, int KEY, bool GATHER>
 static int launch_select(const double* coords, const double* values, int64_t n, const BinTable& tab,
                          const DirParams& dp, const SegTable& seg_tab, int64_t nbuckets,
                          uint64_t* hist, uint64_t* max_bits, const uint32_t* bitmap,
@@ -812,19 +813,14 @@ static int launch_select(const double* coords, const double* values, int64_t n, 
 }
 
 template <bool GATHER, typename... A>
-static int dispatch_select(int dim, bool dir, bool seg, int key, const A&... a) {
+static int dispatch_select(int dim, int dir, bool seg, int key, const A&... a) {
 #define SKG_SEL(D, DR, SG, K) return launch_select<D, DR, SG, K, GATHER>(a...)
-  if (dim == 3) {
-    if (seg) { if (key == SKG_KEY_SQDIST) SKG_SEL(3, false, true, 0); else SKG_SEL(3, false, true, 1); }
-    else     { if (key == SKG_KEY_SQDIST) SKG_SEL(3, false, false, 0); else SKG_SEL(3, false, false, 1); }
-  }
-  if (dir) {
-    if (seg) { if (key == SKG_KEY_SQDIST) SKG_SEL(2, true, true, 0); else SKG_SEL(2, true, true, 1); }
-    else     { if (key == SKG_KEY_SQDIST) SKG_SEL(2, true, false, 0); else SKG_SEL(2, true, false, 1); }
-  }
-  if (seg) { if (key == SKG_KEY_SQDIST) SKG_SEL(2, false, true, 0); else SKG_SEL(2, false, true, 1); }
-  if (key == SKG_KEY_SQDIST) SKG_SEL(2, false, false, 0);
-  SKG_SEL(2, false, false, 1);
+#define SKG_SEL_KEY(D, DR, SG) do { if (key == SKG_KEY_SQDIST) SKG_SEL(D, DR, SG, 0); else SKG_SEL(D, DR, SG, 1); } while (0)
+  if (dim == 3) { if (seg) SKG_SEL_KEY(3, 0, true); else SKG_SEL_KEY(3, 0, false); }
+  if (dir == 1) { if (seg) SKG_SEL_KEY(2, 1, true); else SKG_SEL_KEY(2, 1, false); }
+  if (dir == 2) { if (seg) SKG_SEL_KEY(2, 2, true); else SKG_SEL_KEY(2, 2, false); }
+  if (seg) SKG_SEL_KEY(2, 0, true); else SKG_SEL_KEY(2, 0, false);
+#undef SKG_SEL_KEY
 #undef SKG_SEL
 }
 
@@ -859,11 +855,11 @@ static int select_common(bool gather, const double* coords, const double* values
     host_seg.scale[k] = seg_scale[k];
   }
   if (gather)
-    rc = dispatch_select<true>(dim, dp.model != SKG_DIR_NONE, n_lags > 0, key_kind, coords, values, n,
+    rc = dispatch_select<true>(dim, dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2), n_lags > 0, key_kind, coords, values, n,
                                tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
                                cand_key, cand_slot, cand_count, capacity, t0, t1, st);
   else
-    rc = dispatch_select<false>(dim, dp.model != SKG_DIR_NONE, n_lags > 0, key_kind, coords, values, n,
+    rc = dispatch_select<false>(dim, dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2), n_lags > 0, key_kind, coords, values, n,
                                 tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
                                 cand_key, cand_slot, cand_count, capacity, t0, t1, st);
   return rc;
@@ -909,7 +905,7 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   if (rc) return rc;
   if (tile_end == tile_begin) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool use_dir = dp.model != SKG_DIR_NONE;
+  const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
   const int max_blocks = sm_count() * MAX_GRID_PER_SM;
   unsigned int* counter = nullptr;
   HistPartial* partial = reinterpret_cast<HistPartial*>(reinterpret_cast<unsigned char*>(scratch) + 256);
