@@ -13,6 +13,7 @@
 // d = sqrt(s) exactly (see include/skg_b200.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -720,8 +721,15 @@ static void choose_grid(int64_t tiles, int occ, int64_t* grid_out, int* js_out) 
       const int64_t rounds = (items + g - 1) / g;
       double eff = (double)items / ((double)g * (double)rounds);
       eff *= (g >= (int64_t)sms * k) ? (0.92 + 0.08 * k / occ) : (double)g / ((double)sms * occ);
-      eff *= 1.0 - 0.012 * std::log2((double)cand);  // per-item staging overhead
-      if (eff > best) { best = eff; grid = g; js = cand; }
+      eff *= 1.0 - 0.03 * std::log2((double)cand);  // per-item staging overhead (measured)
+      if (eff > best + 0.004) { best = eff; grid = g; js = cand; }
+    }
+  }
+  if (const char* f = getenv("SKG_FORCE_JS")) {  // developer override: "<js>,<ctas_per_sm>"
+    int fj = 0, fk = 0;
+    if (sscanf(f, "%d,%d", &fj, &fk) == 2 && fj >= 1 && fj <= 16 && fk >= 1) {
+      js = fj;
+      grid = std::min<int64_t>((int64_t)sms * std::min(fk, occ), tiles * js);
     }
   }
   *grid_out = grid;
