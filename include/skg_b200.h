@@ -208,12 +208,19 @@ int skg_krige_build_grid(const double* coords, int64_t n, int dim, const double*
  *   scratch [dev] >= skg_krige_scratch_bytes(max_points) bytes
  *   [target_begin, target_end) sub-range (multi-GPU sharding; outputs indexed
  *   by absolute target id).
+ *   exclude [dev, m] int32 or NULL: sample id that must not be used as a neighbour
+ *   of target t (-1 = none).  Leave-one-out cross validation
+ *   (util/cross_validation.py:9-21 rebuilds an OrdinaryKriging without sample i and
+ *   krigs at its location) is ONE call with targets = samples, exclude[t] = t.
+ *   The solve is a Cholesky factorisation of the covariance form of the system on
+ *   the FP64 tensor cores; targets whose covariance matrix is not positive
+ *   definite in fp64 are re-solved by partial-pivot LU of the original system.
  */
 int64_t skg_krige_scratch_bytes(int max_points);
 int skg_krige(const double* coords, const double* values, int64_t n, int dim,
               const double* grid, const int32_t* cell_start, const int32_t* order,
               const double* targets, int64_t m, int model, const double* model_params,
-              double radius, int min_points, int max_points,
+              double radius, int min_points, int max_points, const int32_t* exclude,
               double* z, double* sigma, int32_t* status,
               void* scratch, int64_t scratch_bytes,
               int64_t target_begin, int64_t target_end, void* stream);

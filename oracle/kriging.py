@@ -130,3 +130,19 @@ def krige(coords, values, targets, model, effective_range, sill, nugget=0.0,
             sigma[t] = sum(b[:-1] * lam[:-1]) + lam[-1]      # Kriging.py:644
             z[t] = lam[:-1].dot(vals)                        # Kriging.py:647
     return z, sigma, status
+
+
+def jacknife_deviations(coords, values, indices, model, effective_range, sill, nugget=0.0,
+                        shape=None, min_points=5, max_points=15):
+    """util/cross_validation.py:9-21 (_interpolate) for every index: delete the sample,
+    krige at its location from the remaining ones, return Z* - Z."""
+    coords = np.asarray(coords, dtype=float)
+    values = np.asarray(values)
+    out = np.empty(len(indices))
+    for k, idx in enumerate(indices):
+        c = np.delete(coords, idx, axis=0)
+        v = np.delete(values, idx, axis=0)
+        z, _, _ = krige(c, v, coords[idx][None, :], model, effective_range, sill, nugget, shape,
+                        min_points, max_points)
+        out[k] = z[0] - values[idx]
+    return out

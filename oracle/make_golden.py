@@ -197,13 +197,54 @@ def make_kriging(skg, ds):
     np.savez_compressed(os.path.join(OUT, "kriging.npz"), **arrays)
 
 
+def make_cross_validation(skg, ds):
+    """Reference jacknife (util/cross_validation.py) deviations and metrics."""
+    from skgstat.util import cross_validation as rcv
+    from itertools import cycle
+    arrays, manifest = {}, []
+    c1000 = random_points(600, 500.0, 2, seed=5)
+    local = dict(ds)
+    local["rnd600"] = (c1000, gaussian_field(c1000, 60.0, seed=5))
+    for dname, model, n, seed in (("pancake300", "spherical", None, 42),
+                                  ("rnd600", "exponential", 250, 7),
+                                  ("rnd400", "spherical", None, 1)):
+        c, v = local[dname]
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = v
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            V = skg.Variogram(c, v, model=model, n_lags=15, maxlag="median")
+            rng = np.random.default_rng(seed=seed)
+            size = n if n is not None else len(c)
+            idx = rng.choice(len(c), replace=False, size=size)
+            dev = np.fromiter(map(rcv._interpolate, idx, cycle([V])), dtype=float)
+            metrics = [V.cross_validate(n=n, metric=m, seed=seed) for m in ("rmse", "mse", "mae")]
+        d = V.describe()
+        key = "cv/%d" % len(manifest)
+        arrays[key + "/indices"] = idx
+        arrays[key + "/deviations"] = dev
+        arrays[key + "/metrics"] = np.asarray(metrics, dtype=float)
+        manifest.append(dict(key=key, dataset=dname, model=model, n=n, seed=seed,
+                             effective_range=float(d["effective_range"]), sill=float(d["sill"]),
+                             nugget=float(d["nugget"])))
+        print(key, dname, "rmse", metrics[0], "nan", int(np.isnan(dev).sum()))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "cross_validation.npz"), **arrays)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    make_variogram(skg, ds)
-    make_directional(skg, ds)
-    make_kriging(skg, ds)
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv"]
+    if "variogram" in which:
+        make_variogram(skg, ds)
+    if "directional" in which:
+        make_directional(skg, ds)
+    if "kriging" in which:
+        make_kriging(skg, ds)
+    if "cv" in which:
+        make_cross_validation(skg, ds)
 
 
 if __name__ == "__main__":

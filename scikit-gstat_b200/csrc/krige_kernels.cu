@@ -173,6 +173,7 @@ struct KrigeArgs {
   int cap;           // candidate list capacity per warp
   int region_bytes;  // per-warp shared region (list, later the matrix)
   int retry_only;    // LU kernel: only targets the Cholesky kernel marked KRIGE_RETRY
+  const int* exclude;  // per target: sample id that must not be a neighbour (-1: none), or NULL
 };
 
 constexpr int KRIGE_RETRY = 3;  // internal: covariance matrix not positive definite in fp64
@@ -264,7 +265,8 @@ __device__ int prune_list(unsigned long long* keys, int* ids, int len, int k, in
 // warp) with the <= max_points nearest samples within the radius and returns their number.
 template <int DIM>
 __device__ __forceinline__ int find_neighbours(const KrigeArgs& a, double tx, double ty, double tw,
-                                               unsigned long long* keys, int* ids, int lane) {
+                                               int excl, unsigned long long* keys, int* ids,
+                                               int lane) {
   const double* __restrict__ X = a.coords;
   const double* __restrict__ Y = a.coords + a.n;
   const double* __restrict__ W = a.coords + 2 * a.n;
@@ -327,7 +329,7 @@ __device__ __forceinline__ int find_neighbours(const KrigeArgs& a, double tx, do
                   s = __dadd_rn(s, __dmul_rn(dw, dw));
                 }
                 d = sqrt(s);  // cdist value, MetricSpace.py:248-253
-                hit = d <= rad;  // MetricSpace.py:61
+                hit = d <= rad && id != excl;  // MetricSpace.py:61 (excl: leave-one-out)
               }
               const unsigned mask = __ballot_sync(0xffffffffu, hit);
               if (hit) {
@@ -389,7 +391,7 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
     const double tx = a.targets[t];
     const double ty = a.targets[a.m + t];
     const double tw = DIM == 3 ? a.targets[2 * a.m + t] : 0.0;
-    const int len = find_neighbours<DIM>(a, tx, ty, tw, keys, ids, lane);
+    const int len = find_neighbours<DIM>(a, tx, ty, tw, a.exclude ? a.exclude[t] : -1, keys, ids, lane);
     __syncwarp();
     const int nn = len;
     if (nn < a.min_points || nn < 1) {  // Kriging.py:579-580 LessPointsError
@@ -617,7 +619,7 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     const double tx = a.targets[t];
     const double ty = a.targets[a.m + t];
     const double tw = DIM == 3 ? a.targets[2 * a.m + t] : 0.0;
-    const int nn = find_neighbours<DIM>(a, tx, ty, tw, keys, ids, lane);
+    const int nn = find_neighbours<DIM>(a, tx, ty, tw, a.exclude ? a.exclude[t] : -1, keys, ids, lane);
     __syncwarp();
     if (nn < a.min_points || nn < 1) {  // Kriging.py:579-580 LessPointsError
       if (lane == 0) {
@@ -892,8 +894,8 @@ int64_t skg_krige_scratch_bytes(int max_points) {
 int skg_krige(const double* coords, const double* values, int64_t n, int dim, const double* grid,
               const int32_t* cell_start, const int32_t* order, const double* targets, int64_t m,
               int model, const double* model_params, double radius, int min_points, int max_points,
-              double* z, double* sigma, int32_t* status, void* scratch, int64_t scratch_bytes,
-              int64_t target_begin, int64_t target_end, void* stream) {
+              const int32_t* exclude, double* z, double* sigma, int32_t* status, void* scratch,
+              int64_t scratch_bytes, int64_t target_begin, int64_t target_end, void* stream) {
   (void)scratch; (void)scratch_bytes;
   if (!coords || !values || !cell_start || !order || !targets || !model_params || !z || !sigma || !status) {
     set_error("NULL argument");
@@ -929,6 +931,7 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
   }
   a.radius = radius; a.min_points = min_points; a.max_points = max_points;
   a.z = z; a.sigma = sigma; a.status = status; a.t0 = target_begin; a.t1 = target_end;
+  a.exclude = exclude;
   if (target_end == target_begin) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int smem_budget = 226 * 1024;

@@ -751,6 +751,14 @@ class Variogram:
     def nrmse(self):
         return self.rmse / np.nanmean(self.experimental)
 
+    def cross_validate(self, method="jacknife", n=None, metric="rmse", seed=None):
+        """Variogram.py:2577-2625: leave-one-out kriging at the sample locations (one
+        batched kernel call, see util/cross_validation.py)."""
+        from .util import cross_validation
+        if method == "jacknife":
+            return cross_validation.jacknife(self, n=n, metric=metric, seed=seed)
+        raise AttributeError("A method '%s' is not implemented." % method)
+
     def clone(self):
         return copy.deepcopy(self)
 

@@ -11,7 +11,7 @@ from .MetricSpace import MetricSpace, MetricSpacePair
 from .Variogram import Variogram
 from .DirectionalVariogram import DirectionalVariogram
 from .Kriging import OrdinaryKriging
-from . import binning, estimators, models  # noqa: F401
+from . import binning, estimators, models, util  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["Variogram", "DirectionalVariogram", "OrdinaryKriging", "MetricSpace",

@@ -48,7 +48,7 @@ SIGNATURES = {
     "skg_krige_build_grid": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p]),
     "skg_krige_scratch_bytes": (_i64, [_int]),
     "skg_krige": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _i64, _int, _p, _dbl, _int, _int,
-                         _p, _p, _p, _p, _i64, _i64, _i64, _p]),
+                         _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
 }
 
 _lib = None

@@ -669,7 +669,8 @@ class KrigeEngine:
         g[6] = dims[2] if len(dims) > 2 else 1
         return g
 
-    def transform(self, targets, model: str, model_params, min_points: int, max_points: int):
+    def transform(self, targets, model: str, model_params, min_points: int, max_points: int,
+                  exclude=None):
         """targets (M, dim) -> (z, sigma, status) numpy arrays for ALL M targets; with a
         process group each rank krigs its contiguous slice and the slices are gathered."""
         t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64))
@@ -681,7 +682,10 @@ class KrigeEngine:
             raise ValueError("model_params = [range, sill, shape, nugget]")
         with torch.cuda.device(self.device):
             tg = to_device(t.T, self.device)
-            z, sigma, status = self.transform_device(tg, m, model, mp, min_points, max_points)
+            ex = None
+            if exclude is not None:
+                ex = to_device(np.ascontiguousarray(exclude, dtype=np.int32), self.device)
+            z, sigma, status = self.transform_device(tg, m, model, mp, min_points, max_points, ex)
             if self.world > 1:
                 b, e = D.shard_range(m, self.rank, self.world)
                 z = D.allgather_varlen(z[b:e], self.group)
@@ -690,7 +694,7 @@ class KrigeEngine:
         return to_host(z), to_host(sigma), to_host(status)
 
     def transform_device(self, targets_soa: torch.Tensor, m: int, model: str, mp: np.ndarray,
-                         min_points: int, max_points: int):
+                         min_points: int, max_points: int, exclude: Optional[torch.Tensor] = None):
         """Device-resident variant: targets_soa is a (dim*M) fp64 CUDA tensor; returns
         device tensors (only this rank's slice [begin, end) is filled)."""
         z = torch.full((m,), float("nan"), dtype=torch.float64, device=self.device)
@@ -702,8 +706,8 @@ class KrigeEngine:
             _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(self.grid),
             _ptr(self.cell_start), _ptr(self.order), _ptr(targets_soa), m,
             _lib.MODEL_IDS[model], _hptr(mp), self.radius, int(min_points), int(max_points),
-            _ptr(z), _ptr(sigma), _ptr(status), _ptr(self._scratch), self._scratch.numel(),
+            _ptr(exclude), _ptr(z), _ptr(sigma), _ptr(status), _ptr(self._scratch), self._scratch.numel(),
             b, e, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         _lib.check(rc, "skg_krige")
-        self.launches += 1 if e > b else 0
+        self.launches += 2 if e > b else 0
         return z, sigma, status

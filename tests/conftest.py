@@ -53,3 +53,8 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+@pytest.fixture(scope="session")
+def golden_cv():
+    return Golden("cross_validation")

@@ -34,3 +34,14 @@ def test_pancake_kriging_known_answer(golden_kriging):
                                            208.75398093840414, 204.76546428916612], rtol=1e-12)
     assert_allclose(g.out(case, "sigma")[:4], [821.5990160593558, 607.4358198357556,
                                                457.6864840412478, 250.3293362582594], rtol=1e-12)
+
+
+def test_jacknife_oracle_matches_reference_golden(golden_cv):
+    """util/cross_validation.py through the oracle vs the live reference's deviations."""
+    g = golden_cv
+    for case in g.manifest:
+        c, v = g.inputs(case["dataset"])
+        idx = g.out(case, "indices")[:60]
+        dev = ok.jacknife_deviations(c, v, idx, case["model"], case["effective_range"],
+                                     case["sill"], case["nugget"])
+        assert_allclose(dev, g.out(case, "deviations")[:60], rtol=1e-8, atol=1e-9, err_msg=str(case))
