@@ -146,6 +146,34 @@ def morton_order(c: np.ndarray) -> np.ndarray:
     return np.argsort(key)
 
 
+def morton_order_device(ct: torch.Tensor) -> torch.Tensor:
+    """Z-order permutation computed on the device (ct: (dim, N) fp64 CUDA tensor).  Input
+    layout plumbing only (a few elementwise torch ops and one sort); the host version
+    `morton_order` produces the same kind of ordering and is used by the CPU tests."""
+    dim, n = ct.shape
+    bits = 21 if dim == 3 else 31
+    key = torch.zeros(n, dtype=torch.int64, device=ct.device)
+    for k in range(dim):
+        row = torch.nan_to_num(ct[k], nan=0.0, posinf=0.0, neginf=0.0)
+        lo = row.min()
+        ext = torch.clamp(row.max() - lo, min=1e-300)
+        v = ((row - lo) * ((2 ** bits - 1) / ext)).to(torch.int64).clamp_(0, 2 ** bits - 1)
+        if dim == 2:
+            v = (v | (v << 16)) & 0x0000FFFF0000FFFF
+            v = (v | (v << 8)) & 0x00FF00FF00FF00FF
+            v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0F
+            v = (v | (v << 2)) & 0x3333333333333333
+            v = (v | (v << 1)) & 0x5555555555555555
+        else:
+            v = (v | (v << 32)) & 0x1F00000000FFFF
+            v = (v | (v << 16)) & 0x1F0000FF0000FF
+            v = (v | (v << 8)) & 0x100F00F00F00F00F
+            v = (v | (v << 4)) & 0x10C30C30C30C30C3
+            v = (v | (v << 2)) & 0x1249249249249249
+        key |= v << k
+    return torch.argsort(key, stable=True)
+
+
 class PairEngine:
     """Pair sweeps over one point set resident in HBM (SoA fp64)."""
 
@@ -162,16 +190,22 @@ class PairEngine:
         self.rank, self.world = D.world(group)
         # sweeps run over a Z-order sorted copy; materialising accessors need the
         # caller's order (condensed index) and use an unsorted copy made on demand
-        self.perm = morton_order(c) if self.n > 64 else np.arange(self.n)
         self._orig_coords = c
-        self._host_coords = np.ascontiguousarray(c[self.perm])
-        self._host_coords_t = np.ascontiguousarray(self._host_coords.T)
-        self._coords_unsorted = None
+        self._perm_host = None
+        self._host_coords_sorted = None
         self._values_unsorted = None
         with torch.cuda.device(self.device):
-            self.coords = to_device(self._host_coords_t, self.device)
+            self._coords_unsorted = to_device(c.T, self.device).view(self.dim, self.n)
+            if self.n > 64:
+                self._perm_dev = morton_order_device(self._coords_unsorted)
+                self.coords = self._coords_unsorted[:, self._perm_dev].contiguous().view(-1)
+            else:
+                self._perm_dev = None
+                self.coords = self._coords_unsorted.reshape(-1)
+            self._coords_unsorted = self._coords_unsorted.reshape(-1)
         self.values = None
-        self._host_values = None
+        self._host_values_sorted = None
+        self._orig_values = None
         self._vmin = self._vmax = 0.0
         if values is not None:
             self.set_values(values)
@@ -188,15 +222,37 @@ class PairEngine:
     def n_pairs(self) -> int:
         return self.n * (self.n - 1) // 2
 
+    @property
+    def perm(self) -> np.ndarray:
+        """sorted position -> caller's index (host copy, fetched on first use)."""
+        if self._perm_host is None:
+            self._perm_host = np.arange(self.n) if self._perm_dev is None \
+                else to_host(self._perm_dev).astype(np.int64)
+        return self._perm_host
+
+    @property
+    def _host_coords(self) -> np.ndarray:
+        if self._host_coords_sorted is None:
+            self._host_coords_sorted = np.ascontiguousarray(self._orig_coords[self.perm])
+        return self._host_coords_sorted
+
+    @property
+    def _host_values(self):
+        if self.values is None:
+            return None
+        if self._host_values_sorted is None:
+            self._host_values_sorted = np.ascontiguousarray(self._orig_values[self.perm])
+        return self._host_values_sorted
+
     def set_values(self, values):
         v = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).ravel()
         if v.size != self.n:
             raise ValueError("values length %d != number of points %d" % (v.size, self.n))
         self._orig_values = v
-        self._values_unsorted = None
-        v = np.ascontiguousarray(v[self.perm])
-        self.values = to_device(v, self.device)
-        self._host_values = v
+        self._values_unsorted = to_device(v, self.device)
+        self.values = self._values_unsorted if self._perm_dev is None \
+            else self._values_unsorted[self._perm_dev].contiguous()
+        self._host_values_sorted = None
         with np.errstate(invalid="ignore"):
             self._vmin = float(np.nanmin(v)) if v.size else 0.0
             self._vmax = float(np.nanmax(v)) if v.size else 0.0
@@ -220,7 +276,7 @@ class PairEngine:
 
     def sq_upper_bound(self) -> float:
         """A value >= every squared pair distance (bounding-box diagonal, padded)."""
-        ct = self._host_coords_t
+        ct = np.ascontiguousarray(self._orig_coords.T)
         ext = np.array([np.nanmax(r) - np.nanmin(r) for r in ct]) if self.n else np.zeros(self.dim)
         ub = float(np.sum(ext * ext)) * (1.0 + 1e-12)
         return ub if ub > 0.0 else 1.0
@@ -561,10 +617,6 @@ class PairEngine:
         thr = None if edges is None else sq_threshold_bits(edges)
         nl = 0 if thr is None else int(thr.size)
         P = self.n_pairs
-        if self._coords_unsorted is None:
-            self._coords_unsorted = to_device(self._orig_coords.T, self.device)
-        if self._values_unsorted is None and self.values is not None:
-            self._values_unsorted = to_device(self._orig_values, self.device)
         out = {}
         if "dist" in want:
             out["dist"] = np.empty(P, dtype=np.float64)
