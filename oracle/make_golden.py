@@ -232,11 +232,20 @@ def make_cross_validation(skg, ds):
     np.savez_compressed(os.path.join(OUT, "cross_validation.npz"), **arrays)
 
 
+def make_api_fixture(skg):
+    """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
+    test_variogram.py::test_fit_lm; data only."""
+    import pandas as pd
+    df = pd.read_csv(os.path.join("/root/reference/skgstat/tests", "sample.csv"))
+    np.savez_compressed(os.path.join(OUT, "ref_sample.npz"),
+                        coords=df[["x", "y"]].values, values=df.z.values)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -245,6 +254,8 @@ def main():
         make_kriging(skg, ds)
     if "cv" in which:
         make_cross_validation(skg, ds)
+    if "api" in which:
+        make_api_fixture(skg)
 
 
 if __name__ == "__main__":

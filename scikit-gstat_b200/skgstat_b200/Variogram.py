@@ -168,7 +168,8 @@ class Variogram:
             raise NotImplementedError("cross / aggregate variograms (2-D values) are the next "
                                       "row of the scope table, not built yet")
         flat = y.ravel()
-        if flat.size == 0 or bool(np.all(flat == flat[0])):  # len(set(values)) < 2, Variogram.py:575
+        self._single_input = flat.size == 0 or bool(np.all(flat == flat[0]))
+        if self._single_input:  # len(set(values)) < 2, Variogram.py:575
             warnings.warn("All input values are the same.")
         self._values = y
         self._values_token = (id(self), Variogram._token_counter)
@@ -532,12 +533,14 @@ class Variogram:
         return self._fit_method
 
     @fit_method.setter
-    def fit_method(self, method):
-        if method not in ("trf", "lm", "manual", None):
-            if method == "ml":
-                raise NotImplementedError("fit_method='ml' is not part of the accelerated path")
-            raise ValueError("fit method has to be one of ['trf', 'lm', 'manual']")
-        self._fit_method = method
+    def fit_method(self, value):
+        """Variogram.py:1334-1353."""
+        if value not in ("lm", "ml", "trf", "manual"):
+            raise AttributeError("fit_method has to be one of ['lm', 'ml', 'trf', 'manual']")
+        if value == "trf" and self._single_input:
+            raise AttributeError("'trf' is bounded and therefore not supported when all values "
+                                 "are the same.")
+        self._fit_method = value
 
     @property
     def fit_sigma(self):
@@ -635,9 +638,23 @@ class Variogram:
         if self._fit_method == "trf":
             self.cof, self.cov = curve_fit(wrapped, _x, _y, method="trf", sigma=sig, p0=p0,
                                            bounds=bounds, **kwargs)
-        else:
+        elif self._fit_method == "lm":
             self.cof, self.cov = curve_fit(wrapped, _x, _y, method="lm", sigma=sig, p0=p0,
                                            **kwargs)
+        else:  # 'ml': maximise the gaussian log-likelihood of the lag means (Variogram.py:1769-1793)
+            from scipy import stats
+            from scipy.optimize import minimize
+            weights = np.ones(_x.size) if sig is None else 1.0 / np.asarray(sig, dtype=float)
+
+            def negative_loglik(params):
+                pred = np.asarray([wrapped(h, *params) for h in _x], dtype=float)
+                return -np.sum(stats.norm.logpdf(pred, loc=_y, scale=1.0) * weights)
+
+            p0 = np.asarray(p0, dtype=float)
+            res = minimize(negative_loglik, p0 * 0.5, method="SLSQP", bounds=[(0, b) for b in p0])
+            if not res.success:
+                raise RuntimeError("Maximum Likelihood could not estimate parameters.")
+            self.cof = res.x
 
     def transform(self, x):
         if self.cof is None:
