@@ -101,3 +101,37 @@ def test_directional_setters_invalidate(skg):
         V.azimuth = 400
     with pytest.raises(ValueError):
         V.tolerance = -1
+
+
+def test_directional_reference_instantiation_tests(skg):
+    """skgstat/tests/test_directionalvariogram.py:17-84 (post-fit known answers and errors)."""
+    np.random.seed(1306)
+    c = np.random.gamma(11, 2, (30, 2))
+    np.random.seed(1306)
+    v = np.random.normal(5, 4, 30)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d = skg.DirectionalVariogram(c, v, normalize=True).describe()
+        np.testing.assert_array_almost_equal(d["normalized_effective_range"], 436., decimal=0)
+        np.testing.assert_array_almost_equal(d["normalized_sill"], 2706., decimal=0)
+        np.testing.assert_array_almost_equal(d["normalized_nugget"], 0., decimal=0)
+        d = skg.DirectionalVariogram(c, v, azimuth=-45, normalize=True).describe()
+        np.testing.assert_array_almost_equal(d["normalized_effective_range"], 23.438, decimal=3)
+        np.testing.assert_array_almost_equal(d["normalized_sill"], 219.406, decimal=3)
+        d = skg.DirectionalVariogram(c, v, tolerance=15, normalize=True).describe()
+        np.testing.assert_array_almost_equal(d["normalized_effective_range"], 435.7, decimal=1)
+        np.testing.assert_array_almost_equal(d["normalized_sill"], 2722.1, decimal=1)
+        d = skg.DirectionalVariogram(c, v, bandwidth=12, normalize=True).describe()
+        for x, y in zip([d[k] for k in ("normalized_effective_range", "normalized_sill",
+                                        "normalized_nugget")], [435.733, 2715.865, 0]):
+            assert abs(x - y) < 5e-4
+    with pytest.raises(ValueError):
+        skg.DirectionalVariogram(c, v, azimuth=360)
+    with pytest.raises(ValueError):
+        skg.DirectionalVariogram(c, v, tolerance=-1)
+    with pytest.raises(ValueError, match="NotAModel is not a valid model."):
+        skg.DirectionalVariogram(c, v, directional_model="NotAModel")
+    with pytest.raises(ValueError, match="The directional model has to be identified"):
+        skg.DirectionalVariogram(c, v, directional_model=5)
+    DV = skg.DirectionalVariogram(c, v, n_lags=5)
+    assert DV.n_lags == 5
