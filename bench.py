@@ -231,6 +231,9 @@ def run_own(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     h2d, d2h = Traffic.h2d // e2e_steps, Traffic.d2h // e2e_steps
     assert np.allclose(exp, V.experimental, rtol=1e-12)
+    krig = None
+    if world == 1 and not args.no_kriging:
+        krig = bench_kriging(skg, args)  # sampled too: the longest loaded stretch of the run
     clocks = sampler.stop()
 
     t = torch.tensor([step_ms, kern_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -266,7 +269,11 @@ def run_own(args):
                             ".experimental"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this
+                         # config, from the committed ncu --set full capture
+                         # (profiles/r1_pair_hist_ncu_summary.txt); algorithmic bytes: 480 600
+                         "traffic": 514816 if world == 1 else None,
                          "kernel": "pair_hist_kernel<2,false,1,true>", "kernel_ms": kern_ms,
                          "flops_per_pair": FLOPS_PER_PAIR,
                          "peak_source": "DFMA chain measured in this run (skg_fp64_peak); "
@@ -280,8 +287,8 @@ def run_own(args):
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": "oracle.dense_variogram on N=6000 points (%d pairs), "
                                          "%.1f s" % (sp, dt)}
-        if not args.no_kriging:
-            out["kriging"] = bench_kriging(skg, args)
+        if krig is not None:
+            out["kriging"] = krig
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -319,7 +326,17 @@ def bench_kriging(skg, args):
     zz = ok.transform(gx, gy)
     e2e_s = time.perf_counter() - t0
     d = V.describe()
+    # CPU baseline: the reference algorithm (oracle port, 1 core) on a bounded sample
+    from oracle import kriging as okr
+    sub = np.random.default_rng(0).choice(m, 400, replace=False)
+    t0 = time.perf_counter()
+    zr, sr, _ = okr.krige(c, v, np.column_stack((gx[sub], gy[sub])), "exponential",
+                          d["effective_range"], d["sill"], d["nugget"], None, 5, 64)
+    cpu_s = time.perf_counter() - t0
+    assert np.allclose(zz[sub], zr, rtol=1e-9, equal_nan=True)
     return {"metric": "kriged points/s", "value": m / (ms * 1e-3), "unit": "points/s",
+            "cpu_baseline": {"value": 400 / cpu_s, "unit": "points/s", "cores": 1, "kind": "port",
+                             "sample": "oracle.krige on 400 random grid nodes, %.1f s" % cpu_s},
             "ms_per_step": ms, "targets": int(m), "samples": 10000, "min_points": 5,
             "max_points": 64, "model": "exponential", "effective_range": d["effective_range"],
             "nan_fraction": float(np.mean(np.isnan(zz))),
