@@ -93,6 +93,12 @@ const char* skg_last_error(void);
 int skg_device_sm_count(int* sm_count);
 int skg_fp64_peak(int iters, double* ms, double* fma_count);
 
+/* Z-order (Morton) key of every point over the box [lo, lo+ext] ([host, dim] each): the pair
+ * sweeps are fastest over spatially sorted points (lanes of a warp then fall into the same
+ * lag classes); results do not depend on the order.  keys [dev, n] uint64 (out). */
+int skg_morton_keys(const double* coords, int64_t n, int dim, const double* lo, const double* ext,
+                    uint64_t* keys, void* stream);
+
 /* Number of SKG_TILE tiles in the pair triangle of n points. */
 int64_t skg_pair_num_tiles(int64_t n);
 

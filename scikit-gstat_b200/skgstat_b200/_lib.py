@@ -34,6 +34,7 @@ SIGNATURES = {
     "skg_last_error": (C.c_char_p, []),
     "skg_device_sm_count": (_int, [C.POINTER(_int)]),
     "skg_fp64_peak": (_int, [_int, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    "skg_morton_keys": (_int, [_p, _i64, _int, _p, _p, _p, _p]),
     "skg_pair_num_tiles": (_i64, [_i64]),
     "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "skg_pair_hist_scratch_bytes": (_i64, [_int]),

@@ -197,7 +197,15 @@ class PairEngine:
         with torch.cuda.device(self.device):
             self._coords_unsorted = to_device(c.T, self.device).view(self.dim, self.n)
             if self.n > 64:
-                self._perm_dev = morton_order_device(self._coords_unsorted)
+                ct = np.ascontiguousarray(c.T)
+                with np.errstate(invalid="ignore"):
+                    lo = np.nan_to_num(np.array([np.nanmin(r) for r in ct]))
+                    ext = np.nan_to_num(np.array([np.nanmax(r) for r in ct]) - lo)
+                keys = torch.empty(self.n, dtype=torch.int64, device=self.device)
+                rc = self.lib.skg_morton_keys(_ptr(self._coords_unsorted), self.n, self.dim,
+                                              _hptr(lo), _hptr(ext), _ptr(keys), self._stream())
+                _lib.check(rc, "skg_morton_keys")
+                self._perm_dev = torch.argsort(keys)  # keys < 2^63: signed order == unsigned order
                 self.coords = self._coords_unsorted[:, self._perm_dev].contiguous().view(-1)
             else:
                 self._perm_dev = None
