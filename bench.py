@@ -207,7 +207,7 @@ def run_own(args):
         e0.record()
         rc = lib.skg_pair_hist(_ptr(eng.coords), _ptr(eng.values), eng.n, eng.dim, None, _hptr(thr),
                                nl, _lib.STAT_SUM_SQ, _ptr(cnt_d), _ptr(sq_d), None, _ptr(scratch),
-                               scratch.numel(), eng.t0, eng.t1, eng._stream())
+                               scratch.numel(), eng.t0, eng.t1, eng.tstride, eng._stream())
         e1.record()
         _lib.check(rc, "skg_pair_hist")
         if i >= 3:
@@ -246,7 +246,7 @@ def run_own(args):
         pk_ms, pk_fma = C.c_double(), C.c_double()
         _lib.check(lib.skg_fp64_peak(4096, C.byref(pk_ms), C.byref(pk_fma)), "skg_fp64_peak")
         peak_tflops = 2.0 * pk_fma.value / (pk_ms.value * 1e-3) / 1e12
-        my_pairs = pairs / world  # the dominant kernel of one rank covers its tile range
+        my_pairs = pairs / world  # the dominant kernel of one rank covers its share of the tiles
         achieved = FLOPS_PER_PAIR * my_pairs / (kern_ms * 1e-3) / 1e12
         alg_bytes = 8.0 * 3 * n + 24.0 * N_LAGS
         out = {

@@ -122,7 +122,7 @@ int64_t skg_pair_num_tiles(int64_t n);
  *               adds their contributions.  This is what skgstat_b200 does. */
 int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const double* dir,
                            int32_t* pair_i, int32_t* pair_j, uint64_t* count, int64_t capacity,
-                           int64_t tile_begin, int64_t tile_end, void* stream);
+                           int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* K2 - fused distance -> lag class -> estimator statistics.
  * Replaces MetricSpace.dists + Variogram.distance + _calc_diff + _calc_groups
@@ -132,15 +132,25 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
  *   count    [dev, n_lags]   += pairs per lag class (exact)
  *   sum_sq   [dev, n_lags]   += sum dz^2          (if stats & SKG_STAT_SUM_SQ)
  *   sum_sqrt [dev, n_lags]   += sum sqrt|dz|      (if stats & SKG_STAT_SUM_SQRT)
- *   scratch  [dev]           >= skg_pair_hist_scratch_bytes(n_lags) bytes
+ *   scratch  [dev]           >= skg_pair_scratch_bytes(n, n_lags) bytes
  * Per-CTA partials are reduced in a fixed order: results are run-to-run
- * reproducible for a given (n, tile range). */
-int64_t skg_pair_hist_scratch_bytes(int n_lags);
+ * reproducible for a given (n, tile selection).
+ *
+ * Tile selection (all pair sweeps): tiles tile_begin, tile_begin + tile_stride, ... below
+ * tile_end.  G GPUs take (rank, ntiles, G): interleaved, hence balanced.
+ *
+ * Tile culling (all pair sweeps with scratch): the coordinates are expected in a
+ * spatially coherent order (Z-order, skg_morton_keys).  Each sweep first computes the
+ * bounding box of every 256-point block and keeps, in ascending order, only the tiles
+ * whose range of squared distances can matter: below the last lag edge (skg_pair_hist),
+ * inside a segment window / possible maximum (select passes).  Exact for ANY point order
+ * - an incoherent order merely culls nothing. */
+int64_t skg_pair_scratch_bytes(int64_t n, int n_lags);
 int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim,
                   const double* dir, const uint64_t* thr_bits, int n_lags, int stats,
                   uint64_t* count, double* sum_sq, double* sum_sqrt,
                   void* scratch, int64_t scratch_bytes,
-                  int64_t tile_begin, int64_t tile_end, void* stream);
+                  int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* K1/K3 - histogram pass of the exact order-statistic search.
  * Replaces np.nanmax / np.median / np.percentile / np.nanpercentile over the
@@ -156,13 +166,15 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
  *   hist     [dev, nseg*n_buckets] uint64 += counts
  *   max_bits [dev, 1] uint64 atomicMax of the key bits over ALL mask-passing
  *            pairs (window ignored); only written when n_lags == 0; may be NULL.
+ *   scratch  [dev] >= skg_pair_scratch_bytes(n, 1) bytes (block boxes + tile list)
  */
 int skg_pair_select_hist(const double* coords, const double* values, int64_t n, int dim,
                          const double* dir, const uint64_t* thr_bits, int n_lags,
                          int key_kind, const uint64_t* seg_lo_bits,
                          const uint64_t* seg_hi_bits, const double* seg_scale,
                          int64_t n_buckets, uint64_t* hist, uint64_t* max_bits,
-                         int64_t tile_begin, int64_t tile_end, void* stream);
+                         void* scratch, int64_t scratch_bytes,
+                         int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* Gather pass: every key whose (segment, bucket) bit is set in `bitmap`
  * ([dev] uint32 words, bit index = g*n_buckets + bucket) is appended to
@@ -175,8 +187,8 @@ int skg_pair_select_gather(const double* coords, const double* values, int64_t n
                            const uint64_t* seg_hi_bits, const double* seg_scale,
                            int64_t n_buckets, const uint32_t* bitmap,
                            double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
-                           int64_t capacity,
-                           int64_t tile_begin, int64_t tile_end, void* stream);
+                           int64_t capacity, void* scratch, int64_t scratch_bytes,
+                           int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* Materialising accessors (Variogram.distance :1202, pairwise_diffs :592-606,
  * lag_groups :1514-1533, DirectionalVariogram._direction_mask :605-624) for the

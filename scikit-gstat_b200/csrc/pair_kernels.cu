@@ -36,7 +36,8 @@ struct TileSmem {
 template <int DIM, class Op>
 __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
                                             const double* __restrict__ values, int64_t n,
-                                            int64_t t0, int64_t t1, TileSmem<DIM>& sm, Op& op) {
+                                            int64_t t0, int64_t t1, int64_t stride,
+                                            TileSmem<DIM>& sm, Op& op) {
   const int tid = threadIdx.x;
   const int64_t nt = (n + TILE - 1) / TILE;
   const double qnan = __longlong_as_double(NAN_BITS);
@@ -44,7 +45,7 @@ __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
   const double* __restrict__ Y = coords + n;
   const double* __restrict__ W = coords + 2 * n;
 
-  for (int64_t t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+  for (int64_t t = t0 + (int64_t)blockIdx.x * stride; t < t1; t += (int64_t)gridDim.x * stride) {
     int I, J;
     tile_decode(t, nt, I, J);
     double xi[RI], yi[RI], wi[RI], zi[RI];
@@ -93,6 +94,147 @@ __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
 __device__ __forceinline__ void load_tables(const BinTable& tab, uint64_t* sThr, uint8_t* sLut) {
   for (int k = threadIdx.x; k < THR_MAX; k += blockDim.x) sThr[k] = tab.thr[k];
   for (int k = threadIdx.x; k < tab.ncell; k += blockDim.x) sLut[k] = tab.lut[k];
+}
+
+// ------------------------------------------------------------ tile culling ---
+//
+// Points are Z-order sorted, so the 256-point blocks are spatially compact.  From the
+// bounding boxes of two blocks the squared distances of all their pairs lie in
+// [dmin2, dmax2]; a tile whose interval misses every window of interest (beyond maxlag;
+// outside the classes that hold a wanted rank; cannot contain the maximum) is dropped
+// before the sweep.  Exact: dropped pairs contribute to nothing (1e-12 relative slack
+// covers the rounding of the box arithmetic).  The surviving tiles are written in
+// ascending order (single-CTA ordered compaction), so the sweep and its fixed-order
+// reductions stay deterministic.
+
+struct CullWindows {
+  int count;       // windows in use
+  int want_max;    // also keep tiles that can hold the maximum squared distance
+  double lo[64];   // inclusive
+  double hi[64];   // exclusive
+};
+
+struct SweepScratch {  // views into the caller's scratch buffer
+  unsigned long long* counters;  // [0] = number of listed tiles
+  double* bbox;                  // [nt][6]: lo x,y,w ; hi x,y,w
+  unsigned int* list;            // surviving tile ids, ascending
+  unsigned char* tail;           // kernel-specific remainder (hist partials)
+  int64_t tail_bytes;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+block_bbox_kernel(const double* __restrict__ coords, int64_t n, double* __restrict__ bbox) {
+  __shared__ double sLo[DIM][8], sHi[DIM][8];
+  const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double inf = __longlong_as_double((long long)INF_BITS);
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) {
+    const double v = i < n ? coords[(int64_t)k * n + i] : __longlong_as_double(NAN_BITS);
+    double lo = (v == v) ? v : inf, hi = (v == v) ? v : -inf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { sLo[k][warp] = lo; sHi[k][warp] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < DIM) {
+    double lo = inf, hi = -inf;
+    for (int w = 0; w < 8; ++w) { lo = fmin(lo, sLo[threadIdx.x][w]); hi = fmax(hi, sHi[threadIdx.x][w]); }
+    bbox[(int64_t)blockIdx.x * 6 + threadIdx.x] = lo;
+    bbox[(int64_t)blockIdx.x * 6 + 3 + threadIdx.x] = hi;
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void tile_range(const double* __restrict__ bbox, int I, int J,
+                                           double& dmin2, double& dmax2) {
+  dmin2 = 0.0; dmax2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) {
+    const double loI = bbox[(int64_t)I * 6 + k], hiI = bbox[(int64_t)I * 6 + 3 + k];
+    const double loJ = bbox[(int64_t)J * 6 + k], hiJ = bbox[(int64_t)J * 6 + 3 + k];
+    const double gap = fmax(0.0, fmax(loJ - hiI, loI - hiJ));
+    const double far = fmax(fabs(hiJ - loI), fabs(hiI - loJ));
+    dmin2 += gap * gap;
+    dmax2 += far * far;
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(1024)
+tile_cull_kernel(const double* __restrict__ bbox, int64_t nt, int64_t t_begin, int64_t t_end,
+                 int64_t t_stride, const __grid_constant__ CullWindows win,
+                 unsigned int* __restrict__ list, unsigned long long* __restrict__ counters) {
+  __shared__ int warp_tot[32];
+  __shared__ long long carry;
+  __shared__ double sMax[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t ntile = t_end > t_begin ? (t_end - t_begin + t_stride - 1) / t_stride : 0;
+  double need = -1.0;  // want_max: a tile matters if dmax2 >= max over tiles of dmin2
+  if (win.want_max) {
+    double m = 0.0;
+    for (int64_t k = tid; k < ntile; k += blockDim.x) {
+      int I, J;
+      tile_decode(t_begin + k * t_stride, nt, I, J);
+      double a, b;
+      tile_range<DIM>(bbox, I, J, a, b);
+      if (a == a && b == b && a <= b) m = fmax(m, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) sMax[warp] = m;
+    __syncthreads();
+    m = sMax[0];
+    for (int w = 1; w < 32; ++w) m = fmax(m, sMax[w]);
+    need = m * (1.0 - 1e-12);
+  }
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < ntile; base += blockDim.x) {
+    const int64_t k = base + tid;
+    int keep = 0;
+    int64_t t = 0;
+    if (k < ntile) {
+      t = t_begin + k * t_stride;
+      int I, J;
+      tile_decode(t, nt, I, J);
+      double a, b;
+      tile_range<DIM>(bbox, I, J, a, b);
+      if (a == a && b == b && a <= b) {  // both blocks hold finite points
+        const double lo = a * (1.0 - 1e-12), hi = b * (1.0 + 1e-12);
+        for (int w = 0; w < win.count; ++w) keep |= (lo < win.hi[w] && hi >= win.lo[w]) ? 1 : 0;
+        if (win.want_max && hi >= need) keep = 1;
+      }
+    }
+    int x = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int v = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += y;
+      }
+      warp_tot[lane] = v;
+    }
+    __syncthreads();
+    const long long pos = carry + (warp ? warp_tot[warp - 1] : 0) + (x - keep);
+    if (keep) list[pos] = (unsigned int)t;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = pos + keep;
+    __syncthreads();
+  }
+  if (tid == 0) counters[0] = (unsigned long long)carry;
 }
 
 // -------------------------------------------------------------- K2: hist ---
@@ -201,7 +343,8 @@ template <int DIM, int DIR, int STATS, int EMAX, bool PRIV>
 __global__ void __launch_bounds__(HB)
 pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                  const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
-                 HistPartial* __restrict__ partial, int64_t t0, int64_t t1, int js) {
+                 HistPartial* __restrict__ partial, const unsigned int* __restrict__ tile_list,
+                 const unsigned long long* __restrict__ tile_count, int js) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
@@ -234,9 +377,11 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
   // Work item = (tile, j-chunk): each tile's j range is cut into `js` chunks so that the
   // static round-robin over the grid stays balanced when there are few tiles per CTA.
   const int jchunk = TILE / js;
-  for (int64_t w = t0 * js + blockIdx.x; w < t1 * js; w += gridDim.x) {
-    const int64_t t = w / js;
-    const int jbeg = (int)(w - t * js) * jchunk;
+  const int64_t nwork = (int64_t)(*tile_count) * js;  // surviving tiles x j-chunks
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t li = w / js;
+    const int64_t t = tile_list[li];
+    const int jbeg = (int)(w - li * js) * jchunk;
     int I, J;
     tile_decode(t, nt, I, J);
     double xi[HR], yi[HR], wi[HR], zi[HR];
@@ -397,7 +542,8 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
                    unsigned long long* __restrict__ hist, unsigned long long* __restrict__ max_bits,
                    const uint32_t* __restrict__ bitmap, double* __restrict__ cand_key,
                    uint32_t* __restrict__ cand_slot, unsigned long long* __restrict__ cand_count,
-                   long long capacity, int64_t t0, int64_t t1, int js) {
+                   long long capacity, const unsigned int* __restrict__ tile_list,
+                   const unsigned long long* __restrict__ tile_count, int js) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
@@ -423,10 +569,12 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
   const double* __restrict__ W = coords + 2 * n;
   unsigned long long local_max = 0ull;
   const int jchunk = TILE / js;
+  const int64_t nwork = (int64_t)(*tile_count) * js;
 
-  for (int64_t w = t0 * js + blockIdx.x; w < t1 * js; w += gridDim.x) {
-    const int64_t t = w / js;
-    const int jbeg = (int)(w - t * js) * jchunk;
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t li = w / js;
+    const int64_t t = tile_list[li];
+    const int jbeg = (int)(w - li * js) * jchunk;
     int I, J;
     tile_decode(t, nt, I, J);
     double xi[HR], yi[HR], wi[HR], zi[HR];
@@ -556,11 +704,11 @@ __global__ void __launch_bounds__(BLOCK)
 pair_dir_ambiguous_kernel(const double* __restrict__ coords, int64_t n,
                           const __grid_constant__ DirParams dp, int* __restrict__ out_i,
                           int* __restrict__ out_j, unsigned long long* __restrict__ count,
-                          long long capacity, int64_t t0, int64_t t1) {
+                          long long capacity, int64_t t0, int64_t t1, int64_t stride) {
   __shared__ TileSmem<2> sm;
   AmbOp op;
   op.dp = &dp; op.out_i = out_i; op.out_j = out_j; op.count = count; op.capacity = capacity;
-  sweep_tiles<2>(coords, nullptr, n, t0, t1, sm, op);
+  sweep_tiles<2>(coords, nullptr, n, t0, t1, stride, sm, op);
 }
 
 // ------------------------------------------------------- materialisation ---
@@ -691,19 +839,67 @@ int build_dir_params(const double* dir, int dim, DirParams* out) {
   return 0;
 }
 
-static int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0, int64_t t1) {
+static int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0, int64_t t1,
+                           int64_t stride = 1) {
   if (!coords || n < 0) { set_error("coords NULL or n < 0"); return SKG_E_BADARG; }
   if (dim != 2 && dim != 3) {
     set_error("dim=%d unsupported (2 or 3; pad 1-D input with a zero column)", dim);
     return SKG_E_UNSUPPORTED;
   }
   const int64_t ntiles = skg_pair_num_tiles(n);
-  if (t0 < 0 || t1 < t0 || t1 > ntiles) {
-    set_error("tile range [%lld, %lld) outside [0, %lld]", (long long)t0, (long long)t1,
-              (long long)ntiles);
+  if (t0 < 0 || t1 < t0 || t1 > ntiles || stride < 1) {
+    set_error("tile range [%lld, %lld) step %lld outside [0, %lld]", (long long)t0, (long long)t1,
+              (long long)stride, (long long)ntiles);
     return SKG_E_BADARG;
   }
+  if (n > 23000000ll) { set_error("n too large for 32-bit tile ids"); return SKG_E_UNSUPPORTED; }
   return 0;
+}
+
+static int64_t sweep_head_bytes(int64_t n) {
+  const int64_t nt = (n + TILE - 1) / TILE;
+  const int64_t ntiles = nt * (nt + 1) / 2;
+  int64_t b = 256 + nt * 6 * 8 + ntiles * 4;
+  return (b + 255) & ~255ll;
+}
+
+static int carve_scratch(void* scratch, int64_t scratch_bytes, int64_t n, int64_t need_tail,
+                         SweepScratch* out) {
+  const int64_t head = sweep_head_bytes(n);
+  if (!scratch || scratch_bytes < head + need_tail) {
+    set_error("scratch too small: need %lld bytes", (long long)(head + need_tail));
+    return SKG_E_SCRATCH;
+  }
+  const int64_t nt = (n + TILE - 1) / TILE;
+  unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+  out->counters = reinterpret_cast<unsigned long long*>(base);
+  out->bbox = reinterpret_cast<double*>(base + 256);
+  out->list = reinterpret_cast<unsigned int*>(base + 256 + nt * 6 * 8);
+  out->tail = base + head;
+  out->tail_bytes = scratch_bytes - head;
+  return 0;
+}
+
+// bounding boxes of the 256-point blocks + ordered list of the tiles worth sweeping
+static int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win,
+                       int64_t t0, int64_t t1, int64_t stride, const SweepScratch& S,
+                       cudaStream_t st) {
+  const int64_t nt = (n + TILE - 1) / TILE;
+  if (dim == 3) {
+    block_bbox_kernel<3><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox);
+    tile_cull_kernel<3><<<1, 1024, 0, st>>>(S.bbox, nt, t0, t1, stride, win, S.list, S.counters);
+  } else {
+    block_bbox_kernel<2><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox);
+    tile_cull_kernel<2><<<1, 1024, 0, st>>>(S.bbox, nt, t0, t1, stride, win, S.list, S.counters);
+  }
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static double bits_to_double(uint64_t b) {
+  double d;
+  std::memcpy(&d, &b, 8);
+  return d;
 }
 
 constexpr int MAX_GRID_PER_SM = 16;
@@ -744,8 +940,8 @@ static size_t hist_smem_bytes(int nb, int stats, bool priv) {
 struct HistLaunch {
   const double* coords; const double* values; int64_t n;
   const BinTable* tab; const DirParams* dp; HistPartial* partial;
-  unsigned int* counter; unsigned long long* out_count; double* out_sq; double* out_rt;
-  int max_blocks; int64_t t0, t1; size_t smem; cudaStream_t st; int* nblocks_out;
+  const unsigned int* list; const unsigned long long* list_count;
+  int max_blocks; int64_t ntiles; size_t smem; cudaStream_t st; int* nblocks_out;
 };
 
 template <int DIM, int DIR, int STATS, int EMAX, bool PRIV>
@@ -763,11 +959,11 @@ static int launch_hist(const HistLaunch& L) {
   occ = std::min(occ, MAX_GRID_PER_SM);
   int64_t grid = 1;
   int js = 1;
-  choose_grid(L.t1 - L.t0, occ, &grid, &js);
+  choose_grid(L.ntiles, occ, &grid, &js);
   grid = std::min<int64_t>(grid, L.max_blocks);
   *L.nblocks_out = (int)grid;
   kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial,
-                                             L.t0, L.t1, js);
+                                             L.list, L.list_count, js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -801,7 +997,8 @@ static int launch_select(const double* coords, const double* values, int64_t n, 
                          const DirParams& dp, const SegTable& seg_tab, int64_t nbuckets,
                          uint64_t* hist, uint64_t* max_bits, const uint32_t* bitmap,
                          double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
-                         int64_t capacity, int64_t t0, int64_t t1, cudaStream_t st) {
+                         int64_t capacity, int64_t ntiles, const unsigned int* list,
+                         const unsigned long long* list_count, cudaStream_t st) {
   const bool e1 = tab.emax <= 1;
   auto kern = e1 ? pair_select_kernel<DIM, DIR, SEG, KEY, GATHER, 1>
                  : pair_select_kernel<DIM, DIR, SEG, KEY, GATHER, 0>;
@@ -810,12 +1007,12 @@ static int launch_select(const double* coords, const double* values, int64_t n, 
   occ = std::max(1, std::min(occ, MAX_GRID_PER_SM));
   int64_t grid = 1;
   int js = 1;
-  choose_grid(t1 - t0, occ, &grid, &js);
+  choose_grid(ntiles, occ, &grid, &js);
   kern<<<(unsigned)grid, HB, 0, st>>>(
       coords, values, n, tab, dp, seg_tab, (long long)nbuckets,
       reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(max_bits),
       bitmap, cand_key, cand_slot, reinterpret_cast<unsigned long long*>(cand_count),
-      (long long)capacity, t0, t1, js);
+      (long long)capacity, list, list_count, js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -832,14 +1029,54 @@ static int dispatch_select(int dim, int dir, bool seg, int key, const A&... a) {
 #undef SKG_SEL
 }
 
+// windows of squared distance in which a select pass can find anything
+static void select_windows(int n_lags, int key_kind, const uint64_t* thr_bits,
+                           const uint64_t* lo_bits, const uint64_t* hi_bits, bool want_max,
+                           CullWindows* w) {
+  std::memset(w, 0, sizeof(*w));
+  w->want_max = want_max ? 1 : 0;
+  const double inf = bits_to_double(INF_BITS);
+  auto add = [&](double lo, double hi) {
+    if (!(hi > lo)) return;
+    if (w->count && lo <= w->hi[w->count - 1]) {  // merge touching / overlapping windows
+      w->hi[w->count - 1] = std::max(w->hi[w->count - 1], hi);
+      return;
+    }
+    if (w->count == 64) { w->hi[63] = std::max(w->hi[63], hi); return; }
+    w->lo[w->count] = lo;
+    w->hi[w->count] = hi;
+    w->count++;
+  };
+  if (n_lags <= 0) {
+    if (hi_bits[0] > lo_bits[0]) {
+      if (key_kind == SKG_KEY_SQDIST)
+        add(bits_to_double(lo_bits[0]), hi_bits[0] > INF_BITS ? inf : bits_to_double(hi_bits[0]));
+      else
+        add(0.0, inf);
+    }
+    return;
+  }
+  for (int g = 0; g < n_lags; ++g) {  // segments are ascending classes of s
+    if (hi_bits[g] <= lo_bits[g]) continue;
+    double lo = g ? bits_to_double(thr_bits[g - 1]) : 0.0;
+    double hi = bits_to_double(thr_bits[g]);
+    if (key_kind == SKG_KEY_SQDIST) {
+      lo = std::max(lo, bits_to_double(lo_bits[g]));
+      hi = std::min(hi, hi_bits[g] > INF_BITS ? inf : bits_to_double(hi_bits[g]));
+    }
+    add(lo, hi);
+  }
+}
+
 static int select_common(bool gather, const double* coords, const double* values, int64_t n,
                          int dim, const double* dir, const uint64_t* thr_bits, int n_lags,
                          int key_kind, const uint64_t* seg_lo_bits, const uint64_t* seg_hi_bits,
                          const double* seg_scale, int64_t n_buckets, uint64_t* hist,
                          uint64_t* max_bits, const uint32_t* bitmap, double* cand_key,
                          uint32_t* cand_slot, uint64_t* cand_count, int64_t capacity,
-                         int64_t t0, int64_t t1, void* stream) {
-  int rc = check_pair_args(coords, n, dim, t0, t1);
+                         void* scratch, int64_t scratch_bytes, int64_t t0, int64_t t1,
+                         int64_t stride, void* stream) {
+  int rc = check_pair_args(coords, n, dim, t0, t1, stride);
   if (rc) return rc;
   if (key_kind != SKG_KEY_SQDIST && key_kind != SKG_KEY_ABSDZ) { set_error("bad key_kind"); return SKG_E_BADARG; }
   if (key_kind == SKG_KEY_ABSDZ && !values) { set_error("values required for |dz| keys"); return SKG_E_BADARG; }
@@ -853,6 +1090,9 @@ static int select_common(bool gather, const double* coords, const double* values
   DirParams dp;
   rc = build_dir_params(dir, dim, &dp);
   if (rc) return rc;
+  SweepScratch S;
+  rc = carve_scratch(scratch, scratch_bytes, n, 0, &S);
+  if (rc) return rc;
   if (t1 == t0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   SegTable host_seg;
@@ -862,14 +1102,22 @@ static int select_common(bool gather, const double* coords, const double* values
     host_seg.hi_bits[k] = seg_hi_bits[k];
     host_seg.scale[k] = seg_scale[k];
   }
+  CullWindows win;
+  select_windows(n_lags, key_kind, thr_bits, seg_lo_bits, seg_hi_bits,
+                 !gather && n_lags <= 0 && max_bits != nullptr, &win);
+  rc = launch_cull(coords, n, dim, win, t0, t1, stride, S, st);
+  if (rc) return rc;
+  const int64_t ntiles = (t1 - t0 + stride - 1) / stride;
   if (gather)
     rc = dispatch_select<true>(dim, dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2), n_lags > 0, key_kind, coords, values, n,
                                tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
-                               cand_key, cand_slot, cand_count, capacity, t0, t1, st);
+                               cand_key, cand_slot, cand_count, capacity, ntiles,
+                               (const unsigned int*)S.list, (const unsigned long long*)S.counters, st);
   else
     rc = dispatch_select<false>(dim, dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2), n_lags > 0, key_kind, coords, values, n,
                                 tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
-                                cand_key, cand_slot, cand_count, capacity, t0, t1, st);
+                                cand_key, cand_slot, cand_count, capacity, ntiles,
+                                (const unsigned int*)S.list, (const unsigned long long*)S.counters, st);
   return rc;
 }
 
@@ -885,26 +1133,28 @@ int64_t skg_pair_num_tiles(int64_t n) {
   return nt * (nt + 1) / 2;
 }
 
-int64_t skg_pair_hist_scratch_bytes(int n_lags) {
+int64_t skg_pair_scratch_bytes(int64_t n, int n_lags) {
   if (n_lags < 1) n_lags = 1;
-  return 256 + (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
+  if (n < 0) n = 0;
+  return sweep_head_bytes(n) +
+         (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
 }
 
 int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim, const double* dir,
                   const uint64_t* thr_bits, int n_lags, int stats, uint64_t* count, double* sum_sq,
                   double* sum_sqrt, void* scratch, int64_t scratch_bytes, int64_t tile_begin,
-                  int64_t tile_end, void* stream) {
-  int rc = check_pair_args(coords, n, dim, tile_begin, tile_end);
+                  int64_t tile_end, int64_t tile_stride, void* stream) {
+  int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
   if (!values || !thr_bits || !count || n_lags < 1) { set_error("values/thr_bits/count NULL or n_lags < 1"); return SKG_E_BADARG; }
   if ((stats & ~3) || ((stats & SKG_STAT_SUM_SQ) && !sum_sq) || ((stats & SKG_STAT_SUM_SQRT) && !sum_sqrt)) {
     set_error("stats flags / output pointers inconsistent");
     return SKG_E_BADARG;
   }
-  if (!scratch || scratch_bytes < skg_pair_hist_scratch_bytes(n_lags)) {
-    set_error("scratch too small: need %lld bytes", (long long)skg_pair_hist_scratch_bytes(n_lags));
-    return SKG_E_SCRATCH;
-  }
+  const int max_blocks = sm_count() * MAX_GRID_PER_SM;
+  SweepScratch S;
+  rc = carve_scratch(scratch, scratch_bytes, n, (int64_t)max_blocks * n_lags * (int64_t)sizeof(HistPartial), &S);
+  if (rc) return rc;
   BinTable tab;
   rc = build_bin_table(thr_bits, n_lags, &tab);
   if (rc) return rc;
@@ -913,16 +1163,19 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   if (rc) return rc;
   if (tile_end == tile_begin) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  // tiles entirely beyond the last lag edge cannot contribute
+  CullWindows win;
+  std::memset(&win, 0, sizeof(win));
+  win.count = 1;
+  win.lo[0] = 0.0;
+  win.hi[0] = bits_to_double(thr_bits[n_lags - 1]);
+  rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, S, st);
+  if (rc) return rc;
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
-  const int max_blocks = sm_count() * MAX_GRID_PER_SM;
-  unsigned int* counter = nullptr;
-  HistPartial* partial = reinterpret_cast<HistPartial*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+  HistPartial* partial = reinterpret_cast<HistPartial*>(S.tail);
   int nblocks = 0;
-  HistLaunch L{coords, values, n, &tab, &dp, partial, counter,
-               reinterpret_cast<unsigned long long*>(count),
-               (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr,
-               (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr,
-               max_blocks, tile_begin, tile_end, 0, st, &nblocks};
+  HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, max_blocks,
+               (tile_end - tile_begin + tile_stride - 1) / tile_stride, 0, st, &nblocks};
   bool priv = true;
   L.smem = hist_smem_bytes(n_lags, stats, true);
   if (L.smem > 180 * 1024) {
@@ -942,11 +1195,12 @@ int skg_pair_select_hist(const double* coords, const double* values, int64_t n, 
                          const double* dir, const uint64_t* thr_bits, int n_lags, int key_kind,
                          const uint64_t* seg_lo_bits, const uint64_t* seg_hi_bits,
                          const double* seg_scale, int64_t n_buckets, uint64_t* hist,
-                         uint64_t* max_bits, int64_t tile_begin, int64_t tile_end, void* stream) {
+                         uint64_t* max_bits, void* scratch, int64_t scratch_bytes,
+                         int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream) {
   if (!hist) { set_error("hist NULL"); return SKG_E_BADARG; }
   return select_common(false, coords, values, n, dim, dir, thr_bits, n_lags, key_kind, seg_lo_bits,
                        seg_hi_bits, seg_scale, n_buckets, hist, max_bits, nullptr, nullptr, nullptr,
-                       nullptr, 0, tile_begin, tile_end, stream);
+                       nullptr, 0, scratch, scratch_bytes, tile_begin, tile_end, tile_stride, stream);
 }
 
 int skg_pair_select_gather(const double* coords, const double* values, int64_t n, int dim,
@@ -954,20 +1208,22 @@ int skg_pair_select_gather(const double* coords, const double* values, int64_t n
                            const uint64_t* seg_lo_bits, const uint64_t* seg_hi_bits,
                            const double* seg_scale, int64_t n_buckets, const uint32_t* bitmap,
                            double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
-                           int64_t capacity, int64_t tile_begin, int64_t tile_end, void* stream) {
+                           int64_t capacity, void* scratch, int64_t scratch_bytes,
+                           int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream) {
   if (!bitmap || !cand_key || !cand_slot || !cand_count || capacity < 0) {
     set_error("gather buffers NULL");
     return SKG_E_BADARG;
   }
   return select_common(true, coords, values, n, dim, dir, thr_bits, n_lags, key_kind, seg_lo_bits,
                        seg_hi_bits, seg_scale, n_buckets, nullptr, nullptr, bitmap, cand_key,
-                       cand_slot, cand_count, capacity, tile_begin, tile_end, stream);
+                       cand_slot, cand_count, capacity, scratch, scratch_bytes, tile_begin, tile_end,
+                       tile_stride, stream);
 }
 
 int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const double* dir,
                            int32_t* pair_i, int32_t* pair_j, uint64_t* count, int64_t capacity,
-                           int64_t tile_begin, int64_t tile_end, void* stream) {
-  int rc = check_pair_args(coords, n, dim, tile_begin, tile_end);
+                           int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream) {
+  int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
   if (!dir || !pair_i || !pair_j || !count || capacity < 0) { set_error("NULL argument"); return SKG_E_BADARG; }
   if (n > 2147483647ll) { set_error("n too large for int32 pair indices"); return SKG_E_UNSUPPORTED; }
@@ -977,10 +1233,11 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
   if (dp.model == SKG_DIR_NONE) { set_error("directional model required"); return SKG_E_BADARG; }
   if (tile_end == tile_begin) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t grid = std::min<int64_t>((int64_t)sm_count() * MAX_GRID_PER_SM, tile_end - tile_begin);
+  const int64_t ntl = (tile_end - tile_begin + tile_stride - 1) / tile_stride;
+  const int64_t grid = std::min<int64_t>((int64_t)sm_count() * MAX_GRID_PER_SM, ntl);
   pair_dir_ambiguous_kernel<<<(unsigned)grid, BLOCK, 0, st>>>(
       coords, n, dp, pair_i, pair_j, reinterpret_cast<unsigned long long*>(count),
-      (long long)capacity, tile_begin, tile_end);
+      (long long)capacity, tile_begin, tile_end, tile_stride);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -36,14 +36,14 @@ SIGNATURES = {
     "skg_fp64_peak": (_int, [_int, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "skg_morton_keys": (_int, [_p, _i64, _int, _p, _p, _p, _p]),
     "skg_pair_num_tiles": (_i64, [_i64]),
-    "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
-    "skg_pair_hist_scratch_bytes": (_i64, [_int]),
+    "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
+    "skg_pair_scratch_bytes": (_i64, [_i64, _int]),
     "skg_pair_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _i64,
-                             _i64, _i64, _p]),
+                             _i64, _i64, _i64, _p]),
     "skg_pair_select_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
-                                    _p, _p, _i64, _i64, _p]),
+                                    _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_select_gather": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
-                                      _p, _p, _p, _p, _i64, _i64, _i64, _p]),
+                                      _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_materialize": (_int, [_p, _p, _i64, _int, _p, _p, _int, _p, _p, _p, _p,
                                     _i64, _i64, _p]),
     "skg_krige_build_grid": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p]),

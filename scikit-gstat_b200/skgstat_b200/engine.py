@@ -218,7 +218,10 @@ class PairEngine:
         if values is not None:
             self.set_values(values)
         self.n_tiles = _lib.num_tiles(self.n)
-        self.t0, self.t1 = D.shard_range(self.n_tiles, self.rank, self.world)
+        # interleaved tile shards: rank r sweeps tiles r, r+world, ... (balanced under culling)
+        self.t0, self.t1, self.tstride = self.rank, self.n_tiles, self.world
+        if self.t0 >= self.t1:
+            self.t0 = self.t1 = 0
         self._scratch = None
         self._buffers = {}
         self._amb_cache = {}
@@ -277,7 +280,7 @@ class PairEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _hist_scratch(self, n_lags):
-        need = int(self.lib.skg_pair_hist_scratch_bytes(int(n_lags)))
+        need = int(self.lib.skg_pair_scratch_bytes(self.n, int(n_lags)))
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._scratch
@@ -299,8 +302,8 @@ class PairEngine:
         Returns (i, j) index arrays, or None for isotropic sweeps / policy 0."""
         if dirp is None or dirp[4] == 0.0:
             return None
-        t0, t1 = (0, self.n_tiles) if all_tiles else (self.t0, self.t1)
-        key = tuple(float(x) for x in dirp) + (t0, t1)
+        t0, t1, ts = (0, self.n_tiles, 1) if all_tiles else (self.t0, self.t1, self.tstride)
+        key = tuple(float(x) for x in dirp) + (t0, t1, ts)
         if key in self._amb_cache:
             return self._amb_cache[key]
         cap = self.AMB_CAPACITY
@@ -310,7 +313,7 @@ class PairEngine:
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_dir_ambiguous(
                 _ptr(self.coords), self.n, self.dim, _hptr(dirp), _ptr(pi), _ptr(pj), _ptr(cnt),
-                cap, t0, t1, self._stream())
+                cap, t0, t1, ts, self._stream())
         _lib.check(rc, "skg_pair_dir_ambiguous")
         self.launches += 1 if t1 > t0 else 0
         got = int(cnt.item())
@@ -363,9 +366,9 @@ class PairEngine:
             rc = self.lib.skg_pair_hist(
                 _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), _hptr(thr),
                 nl, int(stats), _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
-                _ptr(scratch), scratch.numel(), self.t0, self.t1, self._stream())
+                _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
-        self.launches += 1 if self.t1 > self.t0 else 0
+        self.launches += 4 if self.t1 > self.t0 else 0  # boxes, cull, sweep, reduce
         out[:nl] = cnt.to(torch.float64)  # exact: counts < 2^53
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
@@ -387,6 +390,7 @@ class PairEngine:
     def _select_runner(self, key_kind, thr, dirp, n_buckets, collect_max=None):
         nl = 0 if thr is None else int(thr.size)
         nseg = max(nl, 1)
+        scratch = self._hist_scratch(1)
         amb = self.ambiguous_pairs(dirp)
         amb_seg = amb_key = None
         if amb is not None and amb[0].size:
@@ -415,9 +419,10 @@ class PairEngine:
                 rc = self.lib.skg_pair_select_hist(
                     _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
                     _hptr(thr), nl, key_kind, _hptr(lo), _hptr(hi), _hptr(sc), n_buckets,
-                    _ptr(hist), _ptr(mx) if nl == 0 else None, self.t0, self.t1, self._stream())
+                    _ptr(hist), _ptr(mx) if (nl == 0 and collect_max is not None) else None,
+                    _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
             _lib.check(rc, "skg_pair_select_hist")
-            self.launches += 1 if self.t1 > self.t0 else 0
+            self.launches += 3 if self.t1 > self.t0 else 0
             if amb_key is not None and amb_key.size:
                 _, slots = amb_slots(lo, hi, sc)
                 extra = np.bincount(slots, minlength=nseg * n_buckets).astype(np.int64)
@@ -444,10 +449,10 @@ class PairEngine:
                 rc = self.lib.skg_pair_select_gather(
                     _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
                     _hptr(thr), nl, key_kind, _hptr(lo), _hptr(hi), _hptr(sc), n_buckets,
-                    _ptr(bm), _ptr(keys), _ptr(slots), _ptr(cnt), cap, self.t0, self.t1,
-                    self._stream())
+                    _ptr(bm), _ptr(keys), _ptr(slots), _ptr(cnt), cap, _ptr(scratch),
+                    scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
             _lib.check(rc, "skg_pair_select_gather")
-            self.launches += 1 if self.t1 > self.t0 else 0
+            self.launches += 3 if self.t1 > self.t0 else 0
             got = int(cnt.item())
             if got > cap:
                 raise RuntimeError("gather overflow: %d > %d" % (got, cap))
@@ -486,9 +491,9 @@ class PairEngine:
             rc = self.lib.skg_pair_hist(
                 _ptr(self.coords), _ptr(vals), self.n, self.dim, _hptr(dirp), _hptr(thr), nl, 0,
                 _ptr(cnt), None, None, _ptr(scratch), scratch.numel(), self.t0, self.t1,
-                self._stream())
+                self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
-        self.launches += 2 if self.t1 > self.t0 else 0
+        self.launches += 4 if self.t1 > self.t0 else 0
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
             s_bits, _ = self._amb_keys(amb)
@@ -571,15 +576,16 @@ class PairEngine:
         passes): one sweep with an empty histogram window, i.e. no atomics."""
         mx = torch.zeros(1, dtype=torch.int64, device=self.device)
         hist = torch.zeros(1, dtype=torch.int64, device=self.device)
+        scratch = self._hist_scratch(1)
         zero = np.zeros(1, dtype=np.uint64)
         sc = np.zeros(1, dtype=np.float64)
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_select_hist(
                 _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), None, 0,
                 _lib.KEY_SQDIST, _hptr(zero), _hptr(zero), _hptr(sc), 1, _ptr(hist), _ptr(mx),
-                self.t0, self.t1, self._stream())
+                _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_select_hist")
-        self.launches += 1 if self.t1 > self.t0 else 0
+        self.launches += 3 if self.t1 > self.t0 else 0
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
             s_bits, _ = self._amb_keys(amb)
