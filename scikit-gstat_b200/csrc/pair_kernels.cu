@@ -117,14 +117,17 @@ struct CullWindows {
 struct SweepScratch {  // views into the caller's scratch buffer
   unsigned long long* counters;  // [0] = number of listed tiles
   double* bbox;                  // [nt][6]: lo x,y,w ; hi x,y,w
-  unsigned int* list;            // surviving tile ids, ascending
+  double* bbox32;                // [nt*8][6]: boxes of the 32-point sub-blocks
+  unsigned int* list;            // surviving work items, ascending
+  unsigned char* flags;          // one byte per candidate work item
   unsigned char* tail;           // kernel-specific remainder (hist partials)
   int64_t tail_bytes;
 };
 
 template <int DIM>
 __global__ void __launch_bounds__(256)
-block_bbox_kernel(const double* __restrict__ coords, int64_t n, double* __restrict__ bbox) {
+block_bbox_kernel(const double* __restrict__ coords, int64_t n, double* __restrict__ bbox,
+                  double* __restrict__ bbox32) {
   __shared__ double sLo[DIM][8], sHi[DIM][8];
   const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -138,7 +141,11 @@ block_bbox_kernel(const double* __restrict__ coords, int64_t n, double* __restri
       lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) { sLo[k][warp] = lo; sHi[k][warp] = hi; }
+    if (lane == 0) {
+      sLo[k][warp] = lo; sHi[k][warp] = hi;
+      bbox32[((int64_t)blockIdx.x * 8 + warp) * 6 + k] = lo;      // 32-point sub-block boxes
+      bbox32[((int64_t)blockIdx.x * 8 + warp) * 6 + 3 + k] = hi;
+    }
   }
   __syncthreads();
   if (threadIdx.x < DIM) {
@@ -164,53 +171,113 @@ __device__ __forceinline__ void tile_range(const double* __restrict__ bbox, int 
   }
 }
 
+// squared-distance range between the box of a 32-point sub-block and a box held in
+// shared memory (lo[3], hi[3]); used for warp-level culling inside the sweeps
 template <int DIM>
-__global__ void __launch_bounds__(1024)
-tile_cull_kernel(const double* __restrict__ bbox, int64_t nt, int64_t t_begin, int64_t t_end,
-                 int64_t t_stride, const __grid_constant__ CullWindows win,
-                 unsigned int* __restrict__ list, unsigned long long* __restrict__ counters) {
-  __shared__ int warp_tot[32];
-  __shared__ long long carry;
-  __shared__ double sMax[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t ntile = t_end > t_begin ? (t_end - t_begin + t_stride - 1) / t_stride : 0;
-  double need = -1.0;  // want_max: a tile matters if dmax2 >= max over tiles of dmin2
-  if (win.want_max) {
-    double m = 0.0;
-    for (int64_t k = tid; k < ntile; k += blockDim.x) {
-      int I, J;
-      tile_decode(t_begin + k * t_stride, nt, I, J);
-      double a, b;
-      tile_range<DIM>(bbox, I, J, a, b);
-      if (a == a && b == b && a <= b) m = fmax(m, a);
-    }
+__device__ __forceinline__ void subblock_range(const double* __restrict__ bbox32, int64_t sub,
+                                               const double* jbox, double& dmin2, double& dmax2) {
+  dmin2 = 0.0; dmax2 = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) sMax[warp] = m;
-    __syncthreads();
-    m = sMax[0];
-    for (int w = 1; w < 32; ++w) m = fmax(m, sMax[w]);
-    need = m * (1.0 - 1e-12);
+  for (int k = 0; k < DIM; ++k) {
+    const double loI = bbox32[sub * 6 + k], hiI = bbox32[sub * 6 + 3 + k];
+    const double loJ = jbox[k], hiJ = jbox[3 + k];
+    const double gap = fmax(0.0, fmax(loJ - hiI, loI - hiJ));
+    const double far = fmax(fabs(hiJ - loI), fabs(hiI - loJ));
+    dmin2 += gap * gap;
+    dmax2 += far * far;
   }
-  if (tid == 0) carry = 0;
-  __syncthreads();
-  for (int64_t base = 0; base < ntile; base += blockDim.x) {
-    const int64_t k = base + tid;
+}
+
+// box of j-chunk h (TILE/js points) of block J: union of the 32-point sub-block boxes
+template <int DIM>
+__device__ __forceinline__ void chunk_box(const double* __restrict__ bbox32, int J, int h, int js,
+                                          double* box /*[6]*/) {
+  const int jchunk = TILE / js;
+  const int s0 = (h * jchunk) >> 5, s1 = (h * jchunk + jchunk - 1) >> 5;
+  const double inf = __longlong_as_double((long long)INF_BITS);
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) { box[k] = inf; box[3 + k] = -inf; }
+  for (int sb = s0; sb <= s1; ++sb) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      box[k] = fmin(box[k], bbox32[((int64_t)J * 8 + sb) * 6 + k]);
+      box[3 + k] = fmax(box[3 + k], bbox32[((int64_t)J * 8 + sb) * 6 + 3 + k]);
+    }
+  }
+}
+
+// Work item = tile * js + j-chunk.  Three small kernels keep, in ascending order, the items
+// whose range of squared distances (i block box x j chunk box) meets a window (or can hold
+// the maximum): (optional) max over tiles of dmin2, per-item flags (fully parallel),
+// ordered compaction of the flags (one CTA, 4096 flags per step).
+template <int DIM>
+__global__ void tile_need_kernel(const double* __restrict__ bbox, int64_t nt, int64_t t_begin,
+                                 int64_t ntile, int64_t t_stride,
+                                 unsigned long long* __restrict__ counters) {
+  double m = 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ntile;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    int I, J;
+    tile_decode(t_begin + k * t_stride, nt, I, J);
+    double a, b;
+    tile_range<DIM>(bbox, I, J, a, b);
+    if (a == a && b == b && a <= b) m = fmax(m, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&counters[1], (unsigned long long)__double_as_longlong(m));
+}
+
+template <int DIM>
+__global__ void item_flags_kernel(const double* __restrict__ bbox, const double* __restrict__ bbox32,
+                                  int64_t n, int64_t nt, int64_t t_begin, int64_t ntile,
+                                  int64_t t_stride, int js, const __grid_constant__ CullWindows win,
+                                  const unsigned long long* __restrict__ counters,
+                                  unsigned char* __restrict__ flags) {
+  const int64_t nitem = ntile * js;
+  const int jchunk = TILE / js;
+  const double need = win.want_max
+      ? __longlong_as_double((long long)counters[1]) * (1.0 - 1e-12) : 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nitem;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = t_begin + (k / js) * t_stride;
+    const int h = (int)(k % js);
+    int I, J;
+    tile_decode(t, nt, I, J);
     int keep = 0;
-    int64_t t = 0;
-    if (k < ntile) {
-      t = t_begin + k * t_stride;
-      int I, J;
-      tile_decode(t, nt, I, J);
-      double a, b;
-      tile_range<DIM>(bbox, I, J, a, b);
-      if (a == a && b == b && a <= b) {  // both blocks hold finite points
+    if ((int64_t)J * TILE + (int64_t)h * jchunk < n) {  // the chunk holds points
+      double jb[6], a, b;
+      chunk_box<DIM>(bbox32, J, h, js, jb);
+      subblock_range<DIM>(bbox, I, jb, a, b);
+      if (a == a && b == b && a <= b) {
         const double lo = a * (1.0 - 1e-12), hi = b * (1.0 + 1e-12);
         for (int w = 0; w < win.count; ++w) keep |= (lo < win.hi[w] && hi >= win.lo[w]) ? 1 : 0;
         if (win.want_max && hi >= need) keep = 1;
       }
     }
-    int x = keep;
+    flags[k] = (unsigned char)keep;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+item_compact_kernel(const unsigned char* __restrict__ flags, int64_t t_begin, int64_t ntile,
+                    int64_t t_stride, int js, unsigned int* __restrict__ list,
+                    unsigned long long* __restrict__ counters) {
+  __shared__ int warp_tot[32];
+  __shared__ long long carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t nitem = ntile * js;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nitem; base += 4096) {
+    const int64_t k0 = base + (int64_t)tid * 4;
+    int f[4], cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f[q] = (k0 + q < nitem) ? flags[k0 + q] : 0;
+      cnt += f[q];
+    }
+    int x = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -228,10 +295,17 @@ tile_cull_kernel(const double* __restrict__ bbox, int64_t nt, int64_t t_begin, i
       warp_tot[lane] = v;
     }
     __syncthreads();
-    const long long pos = carry + (warp ? warp_tot[warp - 1] : 0) + (x - keep);
-    if (keep) list[pos] = (unsigned int)t;
+    long long pos = carry + (warp ? warp_tot[warp - 1] : 0) + (x - cnt);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (f[q]) {
+        const int64_t k = k0 + q;
+        const int64_t t = t_begin + (k / js) * t_stride;
+        list[pos++] = (unsigned int)(t * js + (k % js));
+      }
+    }
     __syncthreads();
-    if (tid == blockDim.x - 1) carry = pos + keep;
+    if (tid == blockDim.x - 1) carry = pos;
     __syncthreads();
   }
   if (tid == 0) counters[0] = (unsigned long long)carry;
@@ -344,7 +418,9 @@ __global__ void __launch_bounds__(HB)
 pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                  const __grid_constant__ BinTable tab, const __grid_constant__ DirParams dp,
                  HistPartial* __restrict__ partial, const unsigned int* __restrict__ tile_list,
-                 const unsigned long long* __restrict__ tile_count, int js) {
+                 const unsigned long long* __restrict__ tile_count,
+                 const double* __restrict__ bbox, const double* __restrict__ bbox32, double wlo,
+                 double whi, int js) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
@@ -377,13 +453,27 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
   // Work item = (tile, j-chunk): each tile's j range is cut into `js` chunks so that the
   // static round-robin over the grid stays balanced when there are few tiles per CTA.
   const int jchunk = TILE / js;
-  const int64_t nwork = (int64_t)(*tile_count) * js;  // surviving tiles x j-chunks
+  const int64_t nwork = (int64_t)(*tile_count);  // surviving (tile, j-chunk) work items
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-    const int64_t li = w / js;
-    const int64_t t = tile_list[li];
-    const int jbeg = (int)(w - li * js) * jchunk;
+    const unsigned int item = tile_list[w];
+    const int64_t t = item / (unsigned)js;
+    const int jbeg = (int)(item % (unsigned)js) * jchunk;
     int I, J;
     tile_decode(t, nt, I, J);
+    // warp-level culling: this warp's four 32-point sub-blocks against the chunk box
+    bool wact = false;
+    {
+      double jb[6];
+      chunk_box<DIM>(bbox32, J, jbeg / jchunk, js, jb);
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        double a, b;
+        subblock_range<DIM>(bbox32, (int64_t)I * 8 + r * (HB / 32) + (tid >> 5), jb, a, b);
+        wact |= (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+      }
+    }
+    const int64_t jn = n - ((int64_t)J * TILE + jbeg);
+    const int jcount = jn < jchunk ? (jn > 0 ? (int)jn : 0) : jchunk;
     double xi[HR], yi[HR], wi[HR], zi[HR];
 #pragma unroll
     for (int r = 0; r < HR; ++r) {
@@ -394,8 +484,6 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
       wi[r] = (DIM == 3) ? (v ? W[i] : qnan) : 0.0;
       zi[r] = v ? values[i] : 0.0;
     }
-    const int64_t jn = n - ((int64_t)J * TILE + jbeg);
-    const int jcount = jn < jchunk ? (jn > 0 ? (int)jn : 0) : jchunk;
     __syncthreads();  // every read of the previous j chunk is done
     for (int k = tid; k < jcount + 2; k += HB) {  // two NaN entries pad the pipeline tail
       const int64_t j = (int64_t)J * TILE + jbeg + k;
@@ -405,7 +493,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
       sZ[k] = v ? values[j] : 0.0;
     }
     __syncthreads();
-    if (jcount == 0) continue;
+    if (jcount == 0 || !wact) continue;  // warp-uniform; both barriers are already passed
 
     auto body = [&](auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
@@ -543,7 +631,9 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
                    const uint32_t* __restrict__ bitmap, double* __restrict__ cand_key,
                    uint32_t* __restrict__ cand_slot, unsigned long long* __restrict__ cand_count,
                    long long capacity, const unsigned int* __restrict__ tile_list,
-                   const unsigned long long* __restrict__ tile_count, int js) {
+                   const unsigned long long* __restrict__ tile_count,
+                   const double* __restrict__ bbox, const double* __restrict__ bbox32, double wlo,
+                   double whi, int js) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
@@ -569,14 +659,27 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
   const double* __restrict__ W = coords + 2 * n;
   unsigned long long local_max = 0ull;
   const int jchunk = TILE / js;
-  const int64_t nwork = (int64_t)(*tile_count) * js;
+  const int64_t nwork = (int64_t)(*tile_count);
 
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-    const int64_t li = w / js;
-    const int64_t t = tile_list[li];
-    const int jbeg = (int)(w - li * js) * jchunk;
+    const unsigned int item = tile_list[w];
+    const int64_t t = item / (unsigned)js;
+    const int jbeg = (int)(item % (unsigned)js) * jchunk;
     int I, J;
     tile_decode(t, nt, I, J);
+    bool wact = false;
+    {
+      double jb[6];
+      chunk_box<DIM>(bbox32, J, jbeg / jchunk, js, jb);
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        double a, b;
+        subblock_range<DIM>(bbox32, (int64_t)I * 8 + r * (HB / 32) + (tid >> 5), jb, a, b);
+        wact |= (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+      }
+    }
+    const int64_t jn = n - ((int64_t)J * TILE + jbeg);
+    const int jcount = jn < jchunk ? (jn > 0 ? (int)jn : 0) : jchunk;
     double xi[HR], yi[HR], wi[HR], zi[HR];
 #pragma unroll
     for (int r = 0; r < HR; ++r) {
@@ -587,8 +690,6 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
       wi[r] = (DIM == 3) ? (v ? W[i] : qnan) : 0.0;
       zi[r] = (v && values) ? values[i] : 0.0;
     }
-    const int64_t jn = n - ((int64_t)J * TILE + jbeg);
-    const int jcount = jn < jchunk ? (jn > 0 ? (int)jn : 0) : jchunk;
     __syncthreads();
     for (int k = tid; k < jcount + 2; k += HB) {
       const int64_t j = (int64_t)J * TILE + jbeg + k;
@@ -598,7 +699,7 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
       sZ[k] = (v && values) ? values[j] : 0.0;
     }
     __syncthreads();
-    if (jcount == 0) continue;
+    if (jcount == 0 || !wact) continue;
 
     auto body = [&](auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
@@ -856,10 +957,14 @@ static int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0,
   return 0;
 }
 
+constexpr int64_t LIST_SPLIT_CAP = 1 << 22;  // j-splitting only while tiles * js fits this
+
+static int64_t list_entries(int64_t ntiles) { return std::max<int64_t>(ntiles, std::min<int64_t>(ntiles * 16, LIST_SPLIT_CAP)); }
+
 static int64_t sweep_head_bytes(int64_t n) {
   const int64_t nt = (n + TILE - 1) / TILE;
   const int64_t ntiles = nt * (nt + 1) / 2;
-  int64_t b = 256 + nt * 6 * 8 + ntiles * 4;
+  int64_t b = 256 + nt * 6 * 8 + nt * 8 * 6 * 8 + list_entries(ntiles) * 5;
   return (b + 255) & ~255ll;
 }
 
@@ -874,24 +979,49 @@ static int carve_scratch(void* scratch, int64_t scratch_bytes, int64_t n, int64_
   unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
   out->counters = reinterpret_cast<unsigned long long*>(base);
   out->bbox = reinterpret_cast<double*>(base + 256);
-  out->list = reinterpret_cast<unsigned int*>(base + 256 + nt * 6 * 8);
+  out->bbox32 = reinterpret_cast<double*>(base + 256 + nt * 6 * 8);
+  out->list = reinterpret_cast<unsigned int*>(base + 256 + nt * 6 * 8 + nt * 8 * 6 * 8);
+  out->flags = reinterpret_cast<unsigned char*>(out->list) + list_entries(nt * (nt + 1) / 2) * 4;
   out->tail = base + head;
   out->tail_bytes = scratch_bytes - head;
   return 0;
 }
 
 // bounding boxes of the 256-point blocks + ordered list of the tiles worth sweeping
+// j-split: enough (tile, chunk) work items per CTA that culling and the static round-robin
+// stay balanced; bounded by the list capacity carved from the scratch
+static int choose_js(int64_t tiles) {
+  const int64_t want = (int64_t)sm_count() * 6 * 12;
+  int js = 1;
+  while (js < 16 && tiles * js < want && tiles * (js * 2) <= LIST_SPLIT_CAP) js *= 2;
+  if (const char* f = getenv("SKG_FORCE_JS")) {  // developer override
+    const int fj = atoi(f);
+    if (fj >= 1 && fj <= 16 && (fj & (fj - 1)) == 0 && tiles * fj <= LIST_SPLIT_CAP) js = fj;
+  }
+  return js;
+}
+
 static int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win,
-                       int64_t t0, int64_t t1, int64_t stride, const SweepScratch& S,
+                       int64_t t0, int64_t t1, int64_t stride, int js, const SweepScratch& S,
                        cudaStream_t st) {
   const int64_t nt = (n + TILE - 1) / TILE;
+  const int64_t ntile = t1 > t0 ? (t1 - t0 + stride - 1) / stride : 0;
+  const int64_t nitem = ntile * js;
+  const unsigned fb = (unsigned)std::min<int64_t>((nitem + 255) / 256, (int64_t)sm_count() * 8);
+  const unsigned tb = (unsigned)std::min<int64_t>((ntile + 255) / 256, (int64_t)sm_count() * 8);
+  if (win.want_max) SKG_CUDA(cudaMemsetAsync(S.counters + 1, 0, 8, st));
   if (dim == 3) {
-    block_bbox_kernel<3><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox);
-    tile_cull_kernel<3><<<1, 1024, 0, st>>>(S.bbox, nt, t0, t1, stride, win, S.list, S.counters);
+    block_bbox_kernel<3><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32);
+    if (win.want_max) tile_need_kernel<3><<<tb, 256, 0, st>>>(S.bbox, nt, t0, ntile, stride, S.counters);
+    item_flags_kernel<3><<<fb, 256, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride, js, win,
+                                             S.counters, S.flags);
   } else {
-    block_bbox_kernel<2><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox);
-    tile_cull_kernel<2><<<1, 1024, 0, st>>>(S.bbox, nt, t0, t1, stride, win, S.list, S.counters);
+    block_bbox_kernel<2><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32);
+    if (win.want_max) tile_need_kernel<2><<<tb, 256, 0, st>>>(S.bbox, nt, t0, ntile, stride, S.counters);
+    item_flags_kernel<2><<<fb, 256, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride, js, win,
+                                             S.counters, S.flags);
   }
+  item_compact_kernel<<<1, 1024, 0, st>>>(S.flags, t0, ntile, stride, js, S.list, S.counters);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -941,7 +1071,8 @@ struct HistLaunch {
   const double* coords; const double* values; int64_t n;
   const BinTable* tab; const DirParams* dp; HistPartial* partial;
   const unsigned int* list; const unsigned long long* list_count;
-  int max_blocks; int64_t ntiles; size_t smem; cudaStream_t st; int* nblocks_out;
+  const double* bbox; const double* bbox32; double wlo, whi;
+  int max_blocks; int64_t ntiles; int js; size_t smem; cudaStream_t st; int* nblocks_out;
 };
 
 template <int DIM, int DIR, int STATS, int EMAX, bool PRIV>
@@ -957,13 +1088,13 @@ static int launch_hist(const HistLaunch& L) {
   int occ = cached_occ;
   if (occ < 1) { set_error("pair_hist kernel does not fit (smem=%zu)", L.smem); return SKG_E_UNSUPPORTED; }
   occ = std::min(occ, MAX_GRID_PER_SM);
-  int64_t grid = 1;
-  int js = 1;
-  choose_grid(L.ntiles, occ, &grid, &js);
+  const int js = L.js;
+  int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, L.ntiles * js);
   grid = std::min<int64_t>(grid, L.max_blocks);
   *L.nblocks_out = (int)grid;
   kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial,
-                                             L.list, L.list_count, js);
+                                             L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi,
+                                             js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -998,21 +1129,20 @@ static int launch_select(const double* coords, const double* values, int64_t n, 
                          uint64_t* hist, uint64_t* max_bits, const uint32_t* bitmap,
                          double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
                          int64_t capacity, int64_t ntiles, const unsigned int* list,
-                         const unsigned long long* list_count, cudaStream_t st) {
+                         const unsigned long long* list_count, const double* bbox,
+                         const double* bbox32, double wlo, double whi, int js, cudaStream_t st) {
   const bool e1 = tab.emax <= 1;
   auto kern = e1 ? pair_select_kernel<DIM, DIR, SEG, KEY, GATHER, 1>
                  : pair_select_kernel<DIM, DIR, SEG, KEY, GATHER, 0>;
   int occ = 0;
   SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HB, 0));
   occ = std::max(1, std::min(occ, MAX_GRID_PER_SM));
-  int64_t grid = 1;
-  int js = 1;
-  choose_grid(ntiles, occ, &grid, &js);
+  const int64_t grid = std::min<int64_t>((int64_t)sm_count() * occ, ntiles * js);
   kern<<<(unsigned)grid, HB, 0, st>>>(
       coords, values, n, tab, dp, seg_tab, (long long)nbuckets,
       reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(max_bits),
       bitmap, cand_key, cand_slot, reinterpret_cast<unsigned long long*>(cand_count),
-      (long long)capacity, list, list_count, js);
+      (long long)capacity, list, list_count, bbox, bbox32, wlo, whi, js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1105,19 +1235,29 @@ static int select_common(bool gather, const double* coords, const double* values
   CullWindows win;
   select_windows(n_lags, key_kind, thr_bits, seg_lo_bits, seg_hi_bits,
                  !gather && n_lags <= 0 && max_bits != nullptr, &win);
-  rc = launch_cull(coords, n, dim, win, t0, t1, stride, S, st);
-  if (rc) return rc;
   const int64_t ntiles = (t1 - t0 + stride - 1) / stride;
+  const int js = choose_js(ntiles);
+  rc = launch_cull(coords, n, dim, win, t0, t1, stride, js, S, st);
+  if (rc) return rc;
+  // chunk/warp-level culling inside the sweep uses the hull of all windows (and
+  // everything when the maximum is wanted, which only the tile list can narrow)
+  double wlo = 0.0, whi = bits_to_double(INF_BITS);
+  if (!win.want_max) {
+    if (win.count) { wlo = win.lo[0]; whi = win.hi[win.count - 1]; }
+    else { wlo = 1.0; whi = 0.0; }  // nothing to find
+  }
   if (gather)
     rc = dispatch_select<true>(dim, dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2), n_lags > 0, key_kind, coords, values, n,
                                tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
                                cand_key, cand_slot, cand_count, capacity, ntiles,
-                               (const unsigned int*)S.list, (const unsigned long long*)S.counters, st);
+                               (const unsigned int*)S.list, (const unsigned long long*)S.counters,
+                               (const double*)S.bbox, (const double*)S.bbox32, wlo, whi, js, st);
   else
     rc = dispatch_select<false>(dim, dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2), n_lags > 0, key_kind, coords, values, n,
                                 tab, dp, host_seg, n_buckets, hist, max_bits, bitmap,
                                 cand_key, cand_slot, cand_count, capacity, ntiles,
-                                (const unsigned int*)S.list, (const unsigned long long*)S.counters, st);
+                                (const unsigned int*)S.list, (const unsigned long long*)S.counters,
+                                (const double*)S.bbox, (const double*)S.bbox32, wlo, whi, js, st);
   return rc;
 }
 
@@ -1169,13 +1309,15 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   win.count = 1;
   win.lo[0] = 0.0;
   win.hi[0] = bits_to_double(thr_bits[n_lags - 1]);
-  rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, S, st);
+  const int64_t ntl = (tile_end - tile_begin + tile_stride - 1) / tile_stride;
+  const int js = choose_js(ntl);
+  rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, js, S, st);
   if (rc) return rc;
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
   HistPartial* partial = reinterpret_cast<HistPartial*>(S.tail);
   int nblocks = 0;
-  HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, max_blocks,
-               (tile_end - tile_begin + tile_stride - 1) / tile_stride, 0, st, &nblocks};
+  HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, S.bbox, S.bbox32,
+               win.lo[0], win.hi[0], max_blocks, ntl, js, 0, st, &nblocks};
   bool priv = true;
   L.smem = hist_smem_bytes(n_lags, stats, true);
   if (L.smem > 180 * 1024) {

@@ -368,7 +368,7 @@ class PairEngine:
                 nl, int(stats), _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
                 _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
-        self.launches += 4 if self.t1 > self.t0 else 0  # boxes, cull, sweep, reduce
+        self.launches += 5 if self.t1 > self.t0 else 0  # boxes, flags, compact, sweep, reduce
         out[:nl] = cnt.to(torch.float64)  # exact: counts < 2^53
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
@@ -422,7 +422,7 @@ class PairEngine:
                     _ptr(hist), _ptr(mx) if (nl == 0 and collect_max is not None) else None,
                     _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
             _lib.check(rc, "skg_pair_select_hist")
-            self.launches += 3 if self.t1 > self.t0 else 0
+            self.launches += 4 if self.t1 > self.t0 else 0
             if amb_key is not None and amb_key.size:
                 _, slots = amb_slots(lo, hi, sc)
                 extra = np.bincount(slots, minlength=nseg * n_buckets).astype(np.int64)
@@ -452,7 +452,7 @@ class PairEngine:
                     _ptr(bm), _ptr(keys), _ptr(slots), _ptr(cnt), cap, _ptr(scratch),
                     scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
             _lib.check(rc, "skg_pair_select_gather")
-            self.launches += 3 if self.t1 > self.t0 else 0
+            self.launches += 4 if self.t1 > self.t0 else 0
             got = int(cnt.item())
             if got > cap:
                 raise RuntimeError("gather overflow: %d > %d" % (got, cap))
@@ -493,7 +493,7 @@ class PairEngine:
                 _ptr(cnt), None, None, _ptr(scratch), scratch.numel(), self.t0, self.t1,
                 self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
-        self.launches += 4 if self.t1 > self.t0 else 0
+        self.launches += 5 if self.t1 > self.t0 else 0
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
             s_bits, _ = self._amb_keys(amb)
@@ -585,7 +585,7 @@ class PairEngine:
                 _lib.KEY_SQDIST, _hptr(zero), _hptr(zero), _hptr(sc), 1, _ptr(hist), _ptr(mx),
                 _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_select_hist")
-        self.launches += 3 if self.t1 > self.t0 else 0
+        self.launches += 5 if self.t1 > self.t0 else 0
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
             s_bits, _ = self._amb_keys(amb)
