@@ -144,7 +144,9 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
  * bounding box of every 256-point block and keeps, in ascending order, only the tiles
  * whose range of squared distances can matter: below the last lag edge (skg_pair_hist),
  * inside a segment window / possible maximum (select passes).  Exact for ANY point order
- * - an incoherent order merely culls nothing. */
+ * - an incoherent order merely culls nothing.  After a sweep the first four uint64 of
+ * `scratch` hold {surviving work items, -, j-chunks per tile (js), candidate work items};
+ * a work item is 256 x (256/js) pair slots. */
 int64_t skg_pair_scratch_bytes(int64_t n, int n_lags);
 int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim,
                   const double* dir, const uint64_t* thr_bits, int n_lags, int stats,

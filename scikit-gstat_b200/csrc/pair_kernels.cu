@@ -308,7 +308,11 @@ item_compact_kernel(const unsigned char* __restrict__ flags, int64_t t_begin, in
     if (tid == blockDim.x - 1) carry = pos;
     __syncthreads();
   }
-  if (tid == 0) counters[0] = (unsigned long long)carry;
+  if (tid == 0) {
+    counters[0] = (unsigned long long)carry;  // surviving work items
+    counters[2] = (unsigned long long)js;     // j-chunks per tile (for reporting)
+    counters[3] = (unsigned long long)nitem;  // candidate work items before culling
+  }
 }
 
 // -------------------------------------------------------------- K2: hist ---

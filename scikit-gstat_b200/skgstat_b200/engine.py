@@ -285,6 +285,15 @@ class PairEngine:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._scratch
 
+    def last_sweep_info(self):
+        """(surviving work items, candidate work items, pair slots per item) of the last
+        sweep that used this engine's scratch (see include/skg_b200.h, tile culling)."""
+        if self._scratch is None:
+            return None
+        c = self._scratch[:32].view(torch.int64).cpu().numpy()
+        js = max(int(c[2]), 1)
+        return int(c[0]), int(c[3]), _lib.TILE * (_lib.TILE // js)
+
     def sq_upper_bound(self) -> float:
         """A value >= every squared pair distance (bounding-box diagonal, padded)."""
         ct = np.ascontiguousarray(self._orig_coords.T)
