@@ -64,6 +64,8 @@ extern "C" {
 /* estimator statistic flags for skg_pair_hist */
 #define SKG_STAT_SUM_SQ 1   /* sum (dz)^2     - estimators.matheron :66   */
 #define SKG_STAT_SUM_SQRT 2 /* sum |dz|^(1/2) - estimators.cressie  :123  */
+#define SKG_STAT_COUNT_BELOW 4 /* (alone) count pairs with |dz| < dz_lo[lag]: exact rank offsets
+                                  for the windowed Dowd median select; counts land in sum_sq */
 
 /* key kinds for the select passes */
 #define SKG_KEY_SQDIST 0 /* s = squared distance (order statistics of d)       */
@@ -150,6 +152,7 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
 int64_t skg_pair_scratch_bytes(int64_t n, int n_lags);
 int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim,
                   const double* dir, const uint64_t* thr_bits, int n_lags, int stats,
+                  const double* dz_lo /* [host, n_lags] or NULL */,
                   uint64_t* count, double* sum_sq, double* sum_sqrt,
                   void* scratch, int64_t scratch_bytes,
                   int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);

@@ -325,6 +325,10 @@ item_compact_kernel(const unsigned char* __restrict__ flags, int64_t t_begin, in
 // compiler knows accumulator stores cannot alias table/tile loads and is free to
 // hoist the next pairs' loads and fp64 math above them.
 
+struct DzTable {  // per-lag |dz| thresholds of the below-count mode (STATS == 4)
+  double lo[THR_MAX];
+};
+
 struct HistPartial {  // one per (CTA, lag class)
   unsigned long long count;
   double sum_sq;
@@ -380,6 +384,18 @@ __device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
         "mov.b64 tb, t;\n\t"
         "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
         :: "r"(addr), "d"(dz), "r"(pred));
+  } else if (STATS == 4) {
+    // dz carries the 0/1 "below the per-lag |dz| threshold" flag: low word of the first
+    // 8 bytes counts those pairs, low word of the second 8 bytes counts all pairs
+    const int below = dz != 0.0 ? 1 : 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bb, cb;\n\t.reg .b32 lo, hi;\n\t"
+        "setp.ne.s32 p, %2, 0;\n\t"
+        "@p ld.shared.v2.b64 {bb, cb}, [%0];\n\t"
+        "mov.b64 {lo, hi}, bb;\n\tadd.u32 lo, lo, %1;\n\tmov.b64 bb, {lo, hi};\n\t"
+        "mov.b64 {lo, hi}, cb;\n\tadd.u32 lo, lo, 1;\n\tmov.b64 cb, {lo, hi};\n\t"
+        "@p st.shared.v2.b64 [%0], {bb, cb};\n\t}"
+        :: "r"(addr), "r"(below), "r"(pred));
   } else {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 cb;\n\t"
@@ -424,12 +440,13 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
                  HistPartial* __restrict__ partial, const unsigned int* __restrict__ tile_list,
                  const unsigned long long* __restrict__ tile_count,
                  const double* __restrict__ bbox, const double* __restrict__ bbox32, double wlo,
-                 double whi, int js) {
+                 double whi, const __grid_constant__ DzTable dzt, int js) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
   __shared__ uint64_t sThr[THR_MAX];
   __shared__ uint8_t sLut[LUT_MAX];
+  __shared__ double sDzLo[STATS == 4 ? THR_MAX : 1];  // per-lag |dz| thresholds (below-count mode)
   extern __shared__ __align__(16) unsigned char acc_raw[];
 
   constexpr int REC = (STATS == 3) ? 32 : 16;
@@ -440,6 +457,9 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
 
   for (int k = tid; k < THR_MAX; k += HB) sThr[k] = tab.thr[k];
   for (int k = tid; k < tab.ncell; k += HB) sLut[k] = tab.lut[k];
+  if (STATS == 4) {
+    for (int k = tid; k < THR_MAX; k += HB) sDzLo[k] = k < nb ? dzt.lo[k] : 0.0;
+  }
   {
     unsigned long long* z = reinterpret_cast<unsigned long long*>(acc_raw);
     for (int k = tid; k < nb * S * (REC / 8); k += HB) z[k] = 0ull;
@@ -523,6 +543,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
           }
           g[r] = gg;
           dz[r] = zi[r] - zj;
+          if (STATS == 4) dz[r] = (fabs(dz[r]) < sDzLo[min(gg, nb - 1)]) ? 1.0 : 0.0;
         }
       };
       auto accumulate = [&](const int (&g)[HR], const double (&dz)[HR]) {
@@ -570,12 +591,13 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
       for (int k = 0; k < HB / 32; ++k) {
         const unsigned char* rec = acc_raw + (size_t)(gI * HB + lane + 32 * k) * REC;
         c += *reinterpret_cast<const unsigned int*>(rec + 8);  // per-thread counts stay < 2^32
-        if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(rec);
+        if (STATS == 4) a += (double)*reinterpret_cast<const unsigned int*>(rec);
+        else if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(rec);
         if (STATS & SKG_STAT_SUM_SQRT) b += *reinterpret_cast<const double*>(rec + (STATS == 3 ? 16 : 0));
       }
       c = warp_sum(c);
-      if (STATS & SKG_STAT_SUM_SQ) a = warp_sum(a);
-      if (STATS & SKG_STAT_SUM_SQRT) b = warp_sum(b);
+      if ((STATS & SKG_STAT_SUM_SQ) || STATS == 4) a = warp_sum(a);
+      if ((STATS & SKG_STAT_SUM_SQRT) && STATS != 4) b = warp_sum(b);
       if (lane == 0) {
         out[gI].count = c;
         out[gI].sum_sq = a;
@@ -1075,7 +1097,7 @@ struct HistLaunch {
   const double* coords; const double* values; int64_t n;
   const BinTable* tab; const DirParams* dp; HistPartial* partial;
   const unsigned int* list; const unsigned long long* list_count;
-  const double* bbox; const double* bbox32; double wlo, whi;
+  const double* bbox; const double* bbox32; double wlo, whi; const DzTable* dzt;
   int max_blocks; int64_t ntiles; int js; size_t smem; cudaStream_t st; int* nblocks_out;
 };
 
@@ -1098,7 +1120,7 @@ static int launch_hist(const HistLaunch& L) {
   *L.nblocks_out = (int)grid;
   kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial,
                                              L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi,
-                                             js);
+                                             *L.dzt, js);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1109,6 +1131,7 @@ static int dispatch_hist_stats(int stats, const HistLaunch& L) {
     case 0: return launch_hist<DIM, DIR, 0, EMAX, PRIV>(L);
     case 1: return launch_hist<DIM, DIR, 1, EMAX, PRIV>(L);
     case 2: return launch_hist<DIM, DIR, 2, EMAX, PRIV>(L);
+    case 4: return launch_hist<DIM, DIR, 4, EMAX, PRIV>(L);
     default: return launch_hist<DIM, DIR, 3, EMAX, PRIV>(L);
   }
 }
@@ -1285,13 +1308,16 @@ int64_t skg_pair_scratch_bytes(int64_t n, int n_lags) {
 }
 
 int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim, const double* dir,
-                  const uint64_t* thr_bits, int n_lags, int stats, uint64_t* count, double* sum_sq,
-                  double* sum_sqrt, void* scratch, int64_t scratch_bytes, int64_t tile_begin,
-                  int64_t tile_end, int64_t tile_stride, void* stream) {
+                  const uint64_t* thr_bits, int n_lags, int stats, const double* dz_lo,
+                  uint64_t* count, double* sum_sq, double* sum_sqrt, void* scratch,
+                  int64_t scratch_bytes, int64_t tile_begin, int64_t tile_end, int64_t tile_stride,
+                  void* stream) {
   int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
   if (!values || !thr_bits || !count || n_lags < 1) { set_error("values/thr_bits/count NULL or n_lags < 1"); return SKG_E_BADARG; }
-  if ((stats & ~3) || ((stats & SKG_STAT_SUM_SQ) && !sum_sq) || ((stats & SKG_STAT_SUM_SQRT) && !sum_sqrt)) {
+  if (stats == SKG_STAT_COUNT_BELOW) {
+    if (!dz_lo || !sum_sq) { set_error("below-count mode needs dz_lo and sum_sq (receives the counts)"); return SKG_E_BADARG; }
+  } else if ((stats & ~3) || ((stats & SKG_STAT_SUM_SQ) && !sum_sq) || ((stats & SKG_STAT_SUM_SQRT) && !sum_sqrt)) {
     set_error("stats flags / output pointers inconsistent");
     return SKG_E_BADARG;
   }
@@ -1320,11 +1346,16 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
   HistPartial* partial = reinterpret_cast<HistPartial*>(S.tail);
   int nblocks = 0;
+  DzTable dzt;
+  std::memset(&dzt, 0, sizeof(dzt));
+  if (stats == SKG_STAT_COUNT_BELOW)
+    for (int k = 0; k < n_lags; ++k) dzt.lo[k] = dz_lo[k];
   HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, S.bbox, S.bbox32,
-               win.lo[0], win.hi[0], max_blocks, ntl, js, 0, st, &nblocks};
+               win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks};
   bool priv = true;
   L.smem = hist_smem_bytes(n_lags, stats, true);
   if (L.smem > 180 * 1024) {
+    if (stats == SKG_STAT_COUNT_BELOW) { set_error("below-count mode: too many lags for private records"); return SKG_E_UNSUPPORTED; }
     priv = false;
     L.smem = hist_smem_bytes(n_lags, stats, false);
   }
@@ -1332,7 +1363,8 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
   if (rc) return rc;
   pair_hist_reduce_kernel<<<n_lags, 32, 0, st>>>(
       partial, nblocks, n_lags, reinterpret_cast<unsigned long long*>(count),
-      (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr, (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr);
+      ((stats & SKG_STAT_SUM_SQ) || stats == SKG_STAT_COUNT_BELOW) ? sum_sq : nullptr,
+      (stats != SKG_STAT_COUNT_BELOW && (stats & SKG_STAT_SUM_SQRT)) ? sum_sqrt : nullptr);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -18,7 +18,7 @@ MAX_LAGS = 250
 KRIGE_MAX_POINTS = 64
 
 DIR_NONE, DIR_TRIANGLE, DIR_COMPASS = 0, 1, 2
-STAT_SUM_SQ, STAT_SUM_SQRT = 1, 2
+STAT_SUM_SQ, STAT_SUM_SQRT, STAT_COUNT_BELOW = 1, 2, 4
 KEY_SQDIST, KEY_ABSDZ = 0, 1
 MODEL_IDS = dict(spherical=0, exponential=1, gaussian=2, cubic=3, stable=4)
 KRIGE_OK, KRIGE_LESS_POINTS, KRIGE_SINGULAR = 0, 1, 2
@@ -38,7 +38,7 @@ SIGNATURES = {
     "skg_pair_num_tiles": (_i64, [_i64]),
     "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_scratch_bytes": (_i64, [_i64, _int]),
-    "skg_pair_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _i64,
+    "skg_pair_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _i64,
                              _i64, _i64, _i64, _p]),
     "skg_pair_select_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
                                     _p, _p, _p, _i64, _i64, _i64, _i64, _p]),

@@ -223,6 +223,7 @@ class PairEngine:
         if self.t0 >= self.t1:
             self.t0 = self.t1 = 0
         self._scratch = None
+        self._all_finite = None
         self._buffers = {}
         self._amb_cache = {}
         self.n_ambiguous = 0
@@ -374,7 +375,7 @@ class PairEngine:
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_hist(
                 _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), _hptr(thr),
-                nl, int(stats), _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
+                nl, int(stats), None, _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
                 _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
         self.launches += 5 if self.t1 > self.t0 else 0  # boxes, flags, compact, sweep, reduce
@@ -487,6 +488,51 @@ class PairEngine:
         return b
 
     COARSE_CLASSES = 32
+    WINDOWED_SELECT_MIN_PAIRS = 4 * 10 ** 9
+    SELECT_HALF_QUANTILE = 0.025
+
+    def _sq_window_classes(self, rank_fn, dirp, limit, hi_bits):
+        """Class boundaries (bit patterns of s) for the counting sweep of a LARGE problem: narrow
+        windows around the quantiles of the wanted ranks, estimated from a random sub-sample of
+        the points (same seed on every rank).  The counting sweep then culls every tile beyond
+        the last window and the fine/gather sweeps see windows of a few percent of the pairs.
+        Purely a speed device: a rank that falls outside its window lands in one of the gap
+        classes and is resolved there, still exactly."""
+        m = int(min(self.n, max(4000, self.n // 4)))
+        if m >= self.n:
+            return None
+        idx = np.sort(np.random.default_rng(54321).choice(self.n, size=m, replace=False))
+        sub = PairEngine(self._orig_coords[idx], device=self.device)
+        # fractions of the wanted ranks; the totals are proportional up to sampling noise
+        probe = rank_fn(10 ** 9)
+        if not probe or len(probe) > 12:
+            return None
+        fr = sorted(set(min(max(r / 1e9, 0.0), 1.0) for r in probe))
+        q = self.SELECT_HALF_QUANTILE
+
+        def sub_rank_fn(tot):
+            if tot < 2000:
+                return []
+            out = set()
+            for f in fr:
+                out.add(max(0, int((f - q) * tot)))
+                out.add(min(tot - 1, int((f + q) * tot)))
+            return sorted(out)
+
+        vals, tot = sub.sq_order_stats(sub_rank_fn, dirp=dirp, limit=limit)
+        self.launches += sub.launches
+        if not vals:
+            return None
+        spans = []
+        for f in fr:
+            lo = to_bits(vals[max(0, int((f - q) * tot))])
+            hi = to_bits(vals[min(tot - 1, int((f + q) * tot))]) + 1
+            if spans and lo <= spans[-1][1]:      # overlapping windows (e.g. the two median ranks)
+                spans[-1][1] = max(spans[-1][1], hi)
+            else:
+                spans.append([lo, hi])
+        bounds = sorted(set(b for s in spans for b in s if 0 < b < hi_bits))
+        return np.array(bounds + [hi_bits], dtype=np.uint64)
 
     def hist_counts(self, thr: np.ndarray, dirp=None) -> np.ndarray:
         """Exact pair counts per class of squared distance for bit-pattern thresholds
@@ -499,7 +545,7 @@ class PairEngine:
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_hist(
                 _ptr(self.coords), _ptr(vals), self.n, self.dim, _hptr(dirp), _hptr(thr), nl, 0,
-                _ptr(cnt), None, None, _ptr(scratch), scratch.numel(), self.t0, self.t1,
+                None, _ptr(cnt), None, None, _ptr(scratch), scratch.numel(), self.t0, self.t1,
                 self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
         self.launches += 5 if self.t1 > self.t0 else 0
@@ -527,21 +573,45 @@ class PairEngine:
         if limit is not None:
             hi_bits = min(hi_bits, sq_upper_inclusive_bits(limit))
         hi_val = from_bits(hi_bits)
-        C = self.COARSE_CLASSES
-        edges_s = [hi_val * (k + 1) / C for k in range(C - 1)] + [hi_val]
-        thr = np.array([to_bits(x) for x in edges_s], dtype=np.uint64)
-        thr = np.maximum.accumulate(thr)
-        thr[-1] = hi_bits
-        counts = self.hist_counts(thr, dirp)
-        total = int(counts.sum())
-        ranks = sorted(set(int(r) for r in rank_fn(total)))
-        for r in ranks:
-            if not (0 <= r < total):
-                raise ValueError("rank %d outside [0, %d)" % (r, total))
-        if not ranks:
-            return {}, total
-        cum = np.cumsum(counts)
-        cls = np.searchsorted(cum, np.asarray(ranks, dtype=np.int64), side="right")
+
+        def default_classes():
+            C = self.COARSE_CLASSES
+            edges_s = [hi_val * (k + 1) / C for k in range(C - 1)] + [hi_val]
+            t = np.maximum.accumulate(np.array([to_bits(x) for x in edges_s], dtype=np.uint64))
+            t[-1] = hi_bits
+            return t
+
+        # without mask, limit or NaN coordinates the number of keys is known: the counting
+        # sweep can then stop at the last window and cull everything beyond it
+        known_total = None
+        if dirp is None and limit is None:
+            if self._all_finite is None:
+                self._all_finite = bool(np.isfinite(self._orig_coords).all())
+            if self._all_finite:
+                known_total = self.n_pairs
+        thr = None
+        if self.n_pairs >= self.WINDOWED_SELECT_MIN_PAIRS:
+            thr = self._sq_window_classes(rank_fn, dirp, limit, hi_bits)
+            if thr is not None and known_total is not None and thr.size > 1:
+                thr = thr[:-1]  # drop the tail class [last window, upper bound)
+        windowed = thr is not None
+        if thr is None:
+            thr = default_classes()
+        while True:
+            counts = self.hist_counts(thr, dirp)
+            total = known_total if (windowed and known_total is not None) else int(counts.sum())
+            ranks = sorted(set(int(r) for r in rank_fn(total)))
+            for r in ranks:
+                if not (0 <= r < total):
+                    raise ValueError("rank %d outside [0, %d)" % (r, total))
+            if not ranks:
+                return {}, total
+            cum = np.cumsum(counts)
+            cls = np.searchsorted(cum, np.asarray(ranks, dtype=np.int64), side="right")
+            if windowed and (cls >= thr.size).any():
+                thr, windowed = default_classes(), False  # a rank lies beyond the sampled windows
+                continue
+            break
         wanted = sorted(set(int(c) for c in cls))
         # window table: [lo_1, hi_1, lo_2, hi_2, ...]; class 2w+1 = inside window w
         bounds, win_lo, win_hi, base = [], [], [], []
@@ -607,31 +677,137 @@ class PairEngine:
         # bits == 0 means s == 0 for every pair or no pair at all; both give max d = 0 / none
         return from_bits(bits) if bits > 0 else (0.0 if (self.n_pairs > 0 and dirp is None) else None)
 
+    WINDOWED_MEDIAN_MIN_PAIRS = 2 * 10 ** 8   # below this the plain two-sweep select is fast enough
+    WINDOW_HALF_QUANTILE = 0.04
+
+    def _dz_select(self, thr, dirp, lo_bits, hi_bits, rank_fn):
+        nl = int(thr.size)
+        nb = self._buckets_for(self.n_pairs, nl)
+        rh, rg = self._select_runner(_lib.KEY_ABSDZ, thr, dirp, nb)
+        return exact_select(nl, lo_bits, hi_bits, nb, rank_fn, rh, rg)
+
+    def hist_below(self, thr: np.ndarray, dz_lo: np.ndarray, dirp=None):
+        """Exact per-lag (pair count, count of pairs with |dz| < dz_lo[lag]) with the fused-pass
+        kernel (private counters, no atomics); all-reduced over the group."""
+        nl = int(thr.size)
+        cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
+        below = self._buffer("hist_below", nl, torch.float64).zero_()
+        scratch = self._hist_scratch(nl)
+        dz_lo = np.ascontiguousarray(dz_lo, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_hist(
+                _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), _hptr(thr), nl,
+                _lib.STAT_COUNT_BELOW, _hptr(dz_lo), _ptr(cnt), _ptr(below), None, _ptr(scratch),
+                scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
+        _lib.check(rc, "skg_pair_hist")
+        self.launches += 5 if self.t1 > self.t0 else 0
+        both = torch.cat([cnt.to(torch.float64), below])
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, dz = self._amb_keys(amb)
+            g = np.searchsorted(thr, s_bits, side="right")
+            keep = g < nl
+            extra = np.zeros(2 * nl)
+            np.add.at(extra, g[keep], 1.0)
+            np.add.at(extra, nl + g[keep], (dz[keep] < dz_lo[g[keep]]).astype(float))
+            both += to_device(extra, self.device)
+        D.allreduce_sum_(both, self.group)
+        host = to_host(both)
+        return host[:nl].astype(np.int64), host[nl:].astype(np.int64)
+
     def dz_medians(self, edges, dirp=None, thr_bits=None):
         """Per lag class: (count, median |dz|) exactly as np.nanmedian would return
-        over the materialised lag class (estimators.py:178)."""
+        over the materialised lag class (estimators.py:178).
+
+        Small problems: histogram of every in-range |dz| + gather (two sweeps, one L2 atomic
+        per in-range pair).  Large problems: (1) per-lag windows around the median from a
+        random sub-sample of the points; (2) exact per-lag counts and below-window counts with
+        the fused-pass kernel (no atomics); (3)+(4) fine histogram / gather inside the windows
+        only (~8 % of the in-range pairs touch an atomic).  A lag whose window misses the
+        median falls back to the full range, so the result is always exact."""
         if self.values is None:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
         nl = int(thr.size)
         hi = to_bits(abs(self._vmax - self._vmin)) + 1  # fl(zmax - zmin) >= every |dz|
-        nb = self._buckets_for(self.n_pairs, nl)
-        rh, rg = self._select_runner(_lib.KEY_ABSDZ, thr, dirp, nb)
 
         def rank_fn(g, tot):
-            if tot == 0:
-                return []
-            return [(tot - 1) // 2, tot // 2]
+            return [] if tot == 0 else [(tot - 1) // 2, tot // 2]
 
-        vals, totals = exact_select(nl, [0] * nl, [hi] * nl, nb, rank_fn, rh, rg)
+        totals = med_lo = med_hi = None
+        if self.n_pairs >= self.WINDOWED_MEDIAN_MIN_PAIRS and nl * 16 * 64 <= 180 * 1024:
+            win = self._median_windows(thr, dirp, hi)
+            if win is not None:
+                w_lo, w_hi = win                      # per-lag bit windows [lo, hi)
+                dz_lo = w_lo.view(np.float64)
+                counts, below = self.hist_below(thr, dz_lo, dirp)
+                ra = (counts - 1) // 2 - below       # ranks relative to the window start
+                rb = counts // 2 - below
+
+                def rel_rank_fn(g, tot):
+                    if counts[g] == 0 or ra[g] < 0 or rb[g] >= tot:
+                        return []                     # window missed the median: handled below
+                    return [int(ra[g]), int(rb[g])]
+
+                vals, wtot = self._dz_select(thr, dirp, [int(x) for x in w_lo],
+                                             [int(x) for x in w_hi], rel_rank_fn)
+                totals = [int(c) for c in counts]
+                med_lo = [None] * nl
+                med_hi = [None] * nl
+                missed = []
+                for g in range(nl):
+                    if counts[g] == 0:
+                        continue
+                    if ra[g] >= 0 and rb[g] < wtot[g]:
+                        med_lo[g], med_hi[g] = vals[g][int(ra[g])], vals[g][int(rb[g])]
+                    else:
+                        missed.append(g)
+                if missed:  # exact fallback on the full range for those lags only
+                    lo_b = [0] * nl
+                    hi_b = [hi if g in missed else 0 for g in range(nl)]
+                    v2, t2 = self._dz_select(thr, dirp, lo_b, hi_b, rank_fn)
+                    for g in missed:
+                        med_lo[g], med_hi[g] = v2[g][(t2[g] - 1) // 2], v2[g][t2[g] // 2]
+        if totals is None:
+            vals, totals = self._dz_select(thr, dirp, [0] * nl, [hi] * nl, rank_fn)
+            med_lo = [vals[g].get((totals[g] - 1) // 2) if totals[g] else None for g in range(nl)]
+            med_hi = [vals[g].get(totals[g] // 2) if totals[g] else None for g in range(nl)]
         med = np.full(nl, np.nan)
         for g in range(nl):
             t = totals[g]
             if t:
-                a, b = vals[g][(t - 1) // 2], vals[g][t // 2]
+                a, b = med_lo[g], med_hi[g]
                 # np.median: mean of the two middle elements (numpy _median -> mean)
                 med[g] = a if (t % 2) else (a + b) / 2.0
         return np.asarray(totals, dtype=np.int64), med
+
+    def _median_windows(self, thr, dirp, hi_bits_full):
+        """Per-lag |dz| windows (bit patterns) that very probably hold the lag's median: the
+        0.5 -/+ WINDOW_HALF_QUANTILE quantiles of a random sub-sample of the points.  The same
+        sample (fixed seed) on every rank, so all ranks use identical windows."""
+        nl = int(thr.size)
+        m = int(min(self.n, max(4000, self.n // 4)))
+        if m >= self.n:
+            return None
+        idx = np.sort(np.random.default_rng(12345).choice(self.n, size=m, replace=False))
+        sub = PairEngine(self._orig_coords[idx], self._orig_values[idx], device=self.device)
+        q = self.WINDOW_HALF_QUANTILE
+
+        def rank_fn(g, tot):
+            if tot < 400:
+                return []
+            return [max(0, int((0.5 - q) * tot)), min(tot - 1, int((0.5 + q) * tot))]
+
+        vals, totals = sub._dz_select(thr, dirp, [0] * nl, [hi_bits_full] * nl, rank_fn)
+        self.launches += sub.launches
+        w_lo = np.zeros(nl, dtype=np.uint64)
+        w_hi = np.full(nl, hi_bits_full, dtype=np.uint64)
+        for g in range(nl):
+            r = rank_fn(g, totals[g])
+            if r:
+                w_lo[g] = to_bits(vals[g][r[0]])
+                w_hi[g] = to_bits(vals[g][r[1]]) + 1
+        return w_lo, w_hi
 
     # -------------------------------------------------------- materialisation
     def materialize(self, want=("dist",), edges=None, dirp=None, chunk=1 << 24):

@@ -209,3 +209,29 @@ def test_full_size_properties(skg):
     Vs = skg.Variogram(c, 3.0 * v + 7.0, n_lags=25, maxlag="median", fit_method=None)
     assert_array_equal(Vs.bin_count, cnt)
     assert_allclose(Vs.experimental, 9.0 * e1, rtol=1e-11)
+
+
+def test_windowed_select_paths_are_exact(skg, monkeypatch):
+    """The large-problem paths (sample-derived windows for the distance order statistics and
+    for Dowd's per-lag medians) forced on at a size the dense oracle can check."""
+    from skgstat_b200.engine import PairEngine
+    monkeypatch.setattr(PairEngine, "WINDOWED_SELECT_MIN_PAIRS", 0)
+    monkeypatch.setattr(PairEngine, "WINDOWED_MEDIAN_MIN_PAIRS", 0)
+    c = random_points(9000, 1000.0, 2, seed=17)
+    v = gaussian_field(c, 80.0, seed=17)
+    for est, bf, nl, ml in (("dowd", "even", 20, "median"), ("matheron", "uniform", 8, None),
+                            ("dowd", "uniform", 6, 0.4)):
+        ref = ov.dense_variogram(c, v, est, bf, nl, ml)
+        V = skg.Variogram(c, v, estimator=est, bin_func=bf, n_lags=nl, maxlag=ml, fit_method=None)
+        assert_array_equal(V.bins, ref["bins"])
+        assert_array_equal(V.bin_count, ref["bin_count"])
+        assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, equal_nan=True)
+    # heavy ties: lattice coordinates and quantised values
+    gx, gy = np.meshgrid(np.arange(70.0), np.arange(70.0))
+    cl = np.column_stack((gx.ravel(), gy.ravel()))
+    vl = np.round(gaussian_field(cl, 9.0, seed=3), 1)
+    ref = ov.dense_variogram(cl, vl, "dowd", "even", 12, "median")
+    V = skg.Variogram(cl, vl, estimator="dowd", n_lags=12, maxlag="median", fit_method=None)
+    assert_array_equal(V.bins, ref["bins"])
+    assert_array_equal(V.bin_count, ref["bin_count"])
+    assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, equal_nan=True)
