@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SKG_ABI_VERSION 1
+#define SKG_ABI_VERSION 2
 #define SKG_TILE 256            /* points per tile edge                          */
 #define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
 #define SKG_KRIGE_MAX_POINTS 64 /* max_points supported by the warp-per-target kernel */
@@ -66,6 +66,13 @@ extern "C" {
 #define SKG_STAT_SUM_SQRT 2 /* sum |dz|^(1/2) - estimators.cressie  :123  */
 #define SKG_STAT_COUNT_BELOW 4 /* (alone) count pairs with |dz| < dz_lo[lag]: exact rank offsets
                                   for the windowed Dowd median select; counts land in sum_sq */
+
+/* value columns: `values` is [n_values][n] (row per column), value_mode says how the columns of
+ * a pair combine into the "difference" every statistic / |dz| key / diffs output is built from */
+#define SKG_VALUE_SCALAR 0    /* n_values = 1: |z_i - z_j|             (Variogram.py:1938-1943)   */
+#define SKG_VALUE_CROSS 1     /* n_values = 2: |dz_0| * |dz_1|         (:1979-1984 cross-variogram) */
+#define SKG_VALUE_AGGREGATE 2 /* n_values <= 8: sqrt(sum_k dz_k^2)     (:1974-1977 'aggregate')   */
+#define SKG_MAX_VALUE_COLUMNS 8
 
 /* key kinds for the select passes */
 #define SKG_KEY_SQDIST 0 /* s = squared distance (order statistics of d)       */
@@ -150,12 +157,31 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
  * `scratch` hold {surviving work items, -, j-chunks per tile (js), candidate work items};
  * a work item is 256 x (256/js) pair slots. */
 int64_t skg_pair_scratch_bytes(int64_t n, int n_lags);
-int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim,
+int skg_pair_hist(const double* coords, const double* values, int n_values, int value_mode,
+                  int64_t n, int dim,
                   const double* dir, const uint64_t* thr_bits, int n_lags, int stats,
                   const double* dz_lo /* [host, n_lags] or NULL */,
                   uint64_t* count, double* sum_sq, double* sum_sqrt,
                   void* scratch, int64_t scratch_bytes,
                   int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
+
+/* K2b - batched fused pass: the estimator sums of n_vectors value vectors that share the
+ * coordinates, in ceil(n_vectors/4) sweeps (4 vectors per sweep; distance, lag class and pair
+ * count are computed once per pair and sweep).  Replaces the loop of Variogram constructions in
+ * util/uncertainty.py:152-171 (Monte-Carlo propagation) and util/cross_variogram.py:70-85
+ * (diagonal of the grid): same bins, different values.
+ *   values [dev, n_vectors][n]   one row per vector (same point order as coords)
+ *   stat                          SKG_STAT_SUM_SQ or SKG_STAT_SUM_SQRT (one of them)
+ *   count  [dev, n_lags]         += pairs per lag class (identical for every vector)
+ *   sums   [dev, n_vectors][n_lags] += sum dz^2 or sum sqrt|dz| per vector and lag class
+ *   scratch >= skg_pair_batch_scratch_bytes(n, n_lags); n_lags <= skg_pair_batch_max_lags()
+ * Everything else (dir, thr_bits, tiles, culling, determinism) as skg_pair_hist. */
+int skg_pair_batch_max_lags(void);
+int64_t skg_pair_batch_scratch_bytes(int64_t n, int n_lags);
+int skg_pair_hist_batch(const double* coords, const double* values, int n_vectors, int64_t n, int dim,
+                        const double* dir, const uint64_t* thr_bits, int n_lags, int stat,
+                        uint64_t* count, double* sums, void* scratch, int64_t scratch_bytes,
+                        int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* K1/K3 - histogram pass of the exact order-statistic search.
  * Replaces np.nanmax / np.median / np.percentile / np.nanpercentile over the
@@ -173,7 +199,8 @@ int skg_pair_hist(const double* coords, const double* values, int64_t n, int dim
  *            pairs (window ignored); only written when n_lags == 0; may be NULL.
  *   scratch  [dev] >= skg_pair_scratch_bytes(n, 1) bytes (block boxes + tile list)
  */
-int skg_pair_select_hist(const double* coords, const double* values, int64_t n, int dim,
+int skg_pair_select_hist(const double* coords, const double* values, int n_values, int value_mode,
+                         int64_t n, int dim,
                          const double* dir, const uint64_t* thr_bits, int n_lags,
                          int key_kind, const uint64_t* seg_lo_bits,
                          const uint64_t* seg_hi_bits, const double* seg_scale,
@@ -186,7 +213,8 @@ int skg_pair_select_hist(const double* coords, const double* values, int64_t n, 
  * cand_key / cand_slot (slot = g*n_buckets + bucket).  cand_count [dev,1]
  * counts all hits, also those beyond `capacity` (which are dropped; the caller
  * then refines the window and repeats).  Order of candidates is unspecified. */
-int skg_pair_select_gather(const double* coords, const double* values, int64_t n, int dim,
+int skg_pair_select_gather(const double* coords, const double* values, int n_values,
+                           int value_mode, int64_t n, int dim,
                            const double* dir, const uint64_t* thr_bits, int n_lags,
                            int key_kind, const uint64_t* seg_lo_bits,
                            const uint64_t* seg_hi_bits, const double* seg_scale,
@@ -200,7 +228,8 @@ int skg_pair_select_gather(const double* coords, const double* values, int64_t n
  * condensed pair range [pair_begin, pair_end), k = n*i - i(i+1)/2 + (j-i-1).
  * Any output may be NULL.  dist = fl(sqrt(s)) (bit-identical to scipy pdist),
  * diffs = |z_i - z_j|, groups = lag class or -1, mask = 1/0. */
-int skg_pair_materialize(const double* coords, const double* values, int64_t n, int dim,
+int skg_pair_materialize(const double* coords, const double* values, int n_values, int value_mode,
+                         int64_t n, int dim,
                          const double* dir, const uint64_t* thr_bits, int n_lags,
                          double* dist, double* diffs, int64_t* groups, uint8_t* mask,
                          int64_t pair_begin, int64_t pair_end, void* stream);

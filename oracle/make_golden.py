@@ -232,6 +232,94 @@ def make_cross_validation(skg, ds):
     np.savez_compressed(os.path.join(OUT, "cross_validation.npz"), **arrays)
 
 
+def make_multivariate(skg, ds):
+    """Cross-variograms (|dz_0|*|dz_1|), multivariate='aggregate', the cross_variograms grid and
+    the Monte-Carlo propagate utility - Variogram.py:1965-1984, util/cross_variogram.py:61-87,
+    util/uncertainty.py:119-195."""
+    from skgstat.util.cross_variogram import cross_variograms
+    from skgstat.util.uncertainty import propagate
+    arrays, manifest = {}, []
+    mv_sets = {}
+    c, v = ds["rnd400"]
+    rng = np.random.default_rng(11)
+    v2 = 0.6 * v + 0.8 * gaussian_field(c, 20.0, seed=21) + 0.05 * rng.normal(size=len(v))
+    v3 = gaussian_field(c, 6.0, seed=22) + 3.0
+    mv_sets["rnd400"] = (c, np.column_stack((v, v2, v3)))
+    # the reference's own cross-variogram test input (tests/test_variogram.py:1599-1602)
+    np.random.seed(42)
+    cg = np.random.gamma(10, 4, (100, 2))
+    np.random.seed(42)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vg = np.random.multivariate_normal([10.5, 5.6], [[1.5, 3.2], [3.2, 1.5]], size=100)
+    mv_sets["gamma100"] = (cg, vg)
+    c3, v3d = ds["rnd3d150"]
+    mv_sets["rnd3d150"] = (c3, np.column_stack((v3d, gaussian_field(c3, 15.0, seed=23))))
+    for dname, (c, vals) in mv_sets.items():
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = vals
+        for mode in ("cross", "aggregate"):
+            cols = vals[:, :2] if mode == "cross" else vals
+            for est in ("matheron", "cressie", "dowd"):
+                for bf, n_lags, ml in (("even", 10, None), ("uniform", 8, "median"), ("even", 25, "median")):
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        V = skg.Variogram(c, cols, estimator=est, bin_func=bf, n_lags=n_lags,
+                                          maxlag=ml, multivariate=mode)
+                    key = "m/%d" % len(manifest)
+                    arrays[key + "/bins"] = V.bins
+                    arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+                    arrays[key + "/experimental"] = V.experimental
+                    arrays[key + "/diff_checksum"] = np.array([V.pairwise_diffs.sum(), V.pairwise_diffs.max()])
+                    manifest.append(dict(key=key, kind="variogram", dataset=dname, mode=mode,
+                                         estimator=est, bin_func=bf, n_lags=n_lags, maxlag=ml))
+    # directional cross-variograms
+    c, vals = mv_sets["rnd400"]
+    for cfg in (dict(azimuth=45, tolerance=22.5, directional_model="triangle"),
+                dict(azimuth=90, tolerance=60.0, directional_model="compass")):
+        for est in ("matheron", "dowd"):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                V = skg.DirectionalVariogram(c, vals[:, :2], estimator=est, n_lags=8, maxlag="median", **cfg)
+            key = "m/%d" % len(manifest)
+            arrays[key + "/bins"] = V.bins
+            arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+            arrays[key + "/experimental"] = V.experimental
+            manifest.append(dict(key=key, kind="directional", dataset="rnd400", mode="cross",
+                                 estimator=est, n_lags=8, maxlag="median", **cfg))
+    # cross_variograms grid: 3 variables -> 3x3 matrix
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mat = cross_variograms(c, vals, n_lags=12, maxlag="median")
+    key = "m/%d" % len(manifest)
+    arrays[key + "/experimental"] = np.array([[mat[i][j].experimental for j in range(3)] for i in range(3)])
+    arrays[key + "/bin_count"] = np.array([[mat[i][j].bin_count for j in range(3)] for i in range(3)], dtype=np.int64)
+    arrays[key + "/is_cross"] = np.array([[bool(mat[i][j].is_cross_variogram) for j in range(3)] for i in range(3)])
+    manifest.append(dict(key=key, kind="grid", dataset="rnd400", n_lags=12, maxlag="median"))
+    # Monte-Carlo uncertainty propagation (seeded)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        V = skg.Variogram(c, vals[:, 0], n_lags=10, maxlag="median", model="exponential")
+        for est in ("matheron", "cressie"):
+            V.estimator = est
+            ci = propagate(V, "values", sigma=0.3, evalf="experimental", num_iter=40, seed=1234)
+            key = "m/%d" % len(manifest)
+            arrays[key + "/conf"] = np.asarray(ci)
+            manifest.append(dict(key=key, kind="propagate", dataset="rnd400", estimator=est,
+                                 sigma=0.3, num_iter=40, seed=1234, n_lags=10, maxlag="median"))
+        V.estimator = "matheron"
+        res = propagate(V, "values", sigma=0.2, evalf=["experimental", "parameter", "model"],
+                        num_iter=12, seed=7, q=20, eval_at=30)
+        key = "m/%d" % len(manifest)
+        for nm, r in zip(("conf_exp", "conf_par", "conf_model"), res):
+            arrays[key + "/" + nm] = np.asarray(r)
+        manifest.append(dict(key=key, kind="propagate3", dataset="rnd400", sigma=0.2, num_iter=12,
+                             seed=7, q=20, eval_at=30, n_lags=10, maxlag="median"))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "multivariate.npz"), **arrays)
+    print("multivariate cases:", len(manifest))
+
+
 def make_api_fixture(skg):
     """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
     test_variogram.py::test_fit_lm; data only."""
@@ -245,7 +333,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -256,6 +344,8 @@ def main():
         make_cross_validation(skg, ds)
     if "api" in which:
         make_api_fixture(skg)
+    if "multivariate" in which:
+        make_multivariate(skg, ds)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,19 @@ def pairwise_diffs(values) -> np.ndarray:
     return pdist(np.column_stack((v, np.zeros(len(v)))), metric="euclidean")
 
 
+def pairwise_diffs_multi(values, mode) -> np.ndarray:
+    """Variogram.py:1965-1984 for 2-D values: mode 'cross' -> |dz_0| * |dz_1| (values[:, 0] is
+    the observation, values[:, 1] the co-variable, :550-566); mode 'aggregate' ->
+    sqrt(sum_k dz_k^2) with the rows stacked and summed along axis 0 (:1974-1977)."""
+    v = np.asarray(values, dtype=float)
+    if mode == "cross":
+        return pairwise_diffs(v[:, 0]) * pairwise_diffs(v[:, 1])
+    if mode == "aggregate":
+        diffs = np.vstack([pairwise_diffs(v[:, k]) for k in range(v.shape[1])])
+        return np.sqrt(np.sum(diffs ** 2, axis=0))
+    raise ValueError(mode)
+
+
 def resolve_maxlag(d: np.ndarray, maxlag):
     """Variogram.py:1274-1295 (maxlag.setter)."""
     if maxlag is None:
@@ -118,11 +131,15 @@ ESTIMATORS = {"matheron": matheron, "cressie": cressie, "dowd": dowd}
 
 
 def dense_variogram(coordinates, values, estimator="matheron", bin_func="even",
-                    n_lags=10, maxlag=None):
+                    n_lags=10, maxlag=None, multivariate=None):
     """Variogram.py:31-405 (constructor) restricted to the experimental part:
-    returns dict(maxlag, bins, bin_count, experimental)."""
+    returns dict(maxlag, bins, bin_count, experimental).  multivariate: None (1-D values),
+    'cross' or 'aggregate' (2-D values)."""
     d = distance(coordinates)
-    diffs = pairwise_diffs(np.asarray(values, dtype=float))
+    if multivariate is None:
+        diffs = pairwise_diffs(np.asarray(values, dtype=float))
+    else:
+        diffs = pairwise_diffs_multi(values, multivariate)
     ml = resolve_maxlag(d, maxlag)
     edges = BIN_FUNCS[bin_func](d, n_lags, ml)
     g = lag_groups(d, edges)

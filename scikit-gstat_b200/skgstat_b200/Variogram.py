@@ -69,6 +69,10 @@ class Variogram:
         self.multivariate = multivariate
         self.verbose = verbose
         self._reset_pair_state()
+        # set_values decides whether this is a cross / aggregate variogram (Variogram.py:328-332)
+        self._is_cross = None
+        self._co_variable = None
+        self._is_aggregate = None
         self._values = None
         self.set_values(values)
 
@@ -125,7 +129,7 @@ class Variogram:
         # token, not a reference to self: no reference cycle, so device buffers are
         # released as soon as the variogram goes away
         if getattr(eng, "_values_owner", None) != self._values_token or eng.values is None:
-            eng.set_values(self._values)
+            eng.set_values(*self._engine_values())
             eng._values_owner = self._values_token
         return eng
 
@@ -156,7 +160,8 @@ class Variogram:
         self.set_values(values)
 
     def set_values(self, values, calc_diff=True):
-        """Variogram.py:499-590 (1-D observations only)."""
+        """Variogram.py:499-590: 1-D observations, (N, 2) observations + co-variable
+        (cross-variogram, |dz_0|*|dz_1|) or (N, k) with multivariate='aggregate'."""
         if not len(values) == len(self.coordinates):
             raise ValueError("The length of the values array has to match the length of "
                              "coordinates")
@@ -165,8 +170,31 @@ class Variogram:
             raise ValueError("values has to be 1d (classic variogram) or 2d dimensional "
                              "(cross-variogram)")
         if y.ndim == 2:
-            raise NotImplementedError("cross / aggregate variograms (2-D values) are the next "
-                                      "row of the scope table, not built yet")
+            if self.multivariate == "aggregate":
+                warnings.warn("Perform analysis on %d dimension data" % y.ndim)
+                if y.shape[1] > _lib.MAX_VALUE_COLUMNS:
+                    raise NotImplementedError("multivariate='aggregate' supports up to %d columns "
+                                              "on the GPU path" % _lib.MAX_VALUE_COLUMNS)
+                self._is_cross = False
+                self._is_aggregate = True
+            elif self.multivariate == "cross":
+                if y.shape[1] > 2:
+                    raise ValueError("Use the utility function to create a grid of cross-variograms")
+                elif y.shape[1] == 2:
+                    self._co_variable = y[:, 1].flatten()
+                    if self._is_cross is not None and not self._is_cross:
+                        warnings.warn("You passed two variables as observation and effectively "
+                                      "turned this instance into a cross-variogram.")
+                    self._is_cross = True
+                    self._is_aggregate = False
+                    y = y[:, 0].flatten()
+                # (N, 1) falls through unchanged, as in the reference
+            else:
+                raise NotImplementedError("Multivariate mode %s is not implemented for this case."
+                                          % self.multivariate)
+        else:
+            self._is_cross = False
+            self._is_aggregate = False
         flat = y.ravel()
         self._single_input = flat.size == 0 or bool(np.all(flat == flat[0]))
         if self._single_input:  # len(set(values)) < 2, Variogram.py:575
@@ -177,13 +205,24 @@ class Variogram:
         self._diff = None
         self._reset_pair_state()
 
+    def _engine_values(self):
+        """(array, value_mode) handed to the pair engine."""
+        if self._is_cross:
+            return np.column_stack((self._values, self._co_variable)), _lib.VALUE_CROSS
+        if self._is_aggregate:
+            return self._values, _lib.VALUE_AGGREGATE
+        v = self._values
+        return (v[:, 0] if v.ndim == 2 else v), _lib.VALUE_SCALAR
+
     @property
     def is_cross_variogram(self):
-        return False
+        """Read-only flag: cross-variogram (Variogram.py:1468-1471)."""
+        return self._is_cross
 
     @property
     def is_agg_variogram(self):
-        return False
+        """Read-only flag: aggregated multi-column data (Variogram.py:1473-1476)."""
+        return self._is_aggregate
 
     @property
     def n_lags(self):
@@ -409,6 +448,44 @@ class Variogram:
             exp = np.fromiter(map(self._estimator, classes), dtype=float)
         self._bin_count = np.asarray(cnt, dtype=np.int64)
         self._exp = np.asarray(exp, dtype=float)
+
+    def experimental_batch(self, values):
+        """Experimental variograms of K value vectors observed at THIS instance's coordinates,
+        with its bins, estimator and directional mask: values (K, N) -> (K, n_lags).
+
+        matheron / cressie: four vectors share one pair sweep (engine.hist_batch), which is how
+        util.uncertainty.propagate and the diagonal of util.cross_variogram.cross_variograms
+        avoid re-running the distance / lag-class work per vector.  Other estimators fall back
+        to one pass per vector."""
+        V = np.asarray(values, dtype=float)
+        if V.ndim != 2 or V.shape[1] != len(self.coordinates):
+            raise ValueError("values must have shape (K, %d)" % len(self.coordinates))
+        edges = self.bins
+        thr = sq_threshold_bits(edges)
+        eng = self._X.engine(self._process_group)
+        name = self._estimator_name
+        if name in ("matheron", "cressie") and len(edges) <= eng.lib.skg_pair_batch_max_lags():
+            stat = _lib.STAT_SUM_SQ if name == "matheron" else _lib.STAT_SUM_SQRT
+            cnt, sums = eng.hist_batch(edges, V, stat, self._dirp(), thr_bits=thr)
+            fin = estimators.finalize_matheron if name == "matheron" else estimators.finalize_cressie
+            return np.vstack([fin(cnt, sums[k]) for k in range(V.shape[0])])
+        out = np.empty((V.shape[0], len(edges)))
+        keep = (self._values, self._co_variable, self._is_cross, self._is_aggregate, self._exp,
+                self._bin_count, self.cof, self.cov, self._values_token, self._diff, self._groups)
+        try:
+            for k in range(V.shape[0]):
+                self._is_cross, self._is_aggregate, self._co_variable = False, False, None
+                self._values = V[k]
+                self._values_token = (id(self), Variogram._token_counter)
+                Variogram._token_counter += 1
+                self._exp = None
+                self._diff = None
+                self._calc_experimental()
+                out[k] = self._exp
+        finally:
+            (self._values, self._co_variable, self._is_cross, self._is_aggregate, self._exp,
+             self._bin_count, self.cof, self.cov, self._values_token, self._diff, self._groups) = keep
+        return out
 
     @property
     def bin_count(self):

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libskg_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 TILE = 256
 MAX_LAGS = 250
 KRIGE_MAX_POINTS = 64
@@ -20,6 +20,8 @@ KRIGE_MAX_POINTS = 64
 DIR_NONE, DIR_TRIANGLE, DIR_COMPASS = 0, 1, 2
 STAT_SUM_SQ, STAT_SUM_SQRT, STAT_COUNT_BELOW = 1, 2, 4
 KEY_SQDIST, KEY_ABSDZ = 0, 1
+VALUE_SCALAR, VALUE_CROSS, VALUE_AGGREGATE = 0, 1, 2
+MAX_VALUE_COLUMNS = 8
 MODEL_IDS = dict(spherical=0, exponential=1, gaussian=2, cubic=3, stable=4)
 KRIGE_OK, KRIGE_LESS_POINTS, KRIGE_SINGULAR = 0, 1, 2
 
@@ -38,13 +40,17 @@ SIGNATURES = {
     "skg_pair_num_tiles": (_i64, [_i64]),
     "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_scratch_bytes": (_i64, [_i64, _int]),
-    "skg_pair_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _i64,
+    "skg_pair_hist": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _i64,
                              _i64, _i64, _i64, _p]),
-    "skg_pair_select_hist": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
+    "skg_pair_batch_max_lags": (_int, []),
+    "skg_pair_batch_scratch_bytes": (_i64, [_i64, _int]),
+    "skg_pair_hist_batch": (_int, [_p, _p, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
+                                   _i64, _i64, _i64, _p]),
+    "skg_pair_select_hist": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
                                     _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
-    "skg_pair_select_gather": (_int, [_p, _p, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
+    "skg_pair_select_gather": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
                                       _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p]),
-    "skg_pair_materialize": (_int, [_p, _p, _i64, _int, _p, _p, _int, _p, _p, _p, _p,
+    "skg_pair_materialize": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _p, _p, _p, _p,
                                     _i64, _i64, _p]),
     "skg_krige_build_grid": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p]),
     "skg_krige_scratch_bytes": (_i64, [_int]),

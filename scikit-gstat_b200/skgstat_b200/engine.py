@@ -177,7 +177,7 @@ def morton_order_device(ct: torch.Tensor) -> torch.Tensor:
 class PairEngine:
     """Pair sweeps over one point set resident in HBM (SoA fp64)."""
 
-    def __init__(self, coords, values=None, device=None, group=None):
+    def __init__(self, coords, values=None, device=None, group=None, value_mode=_lib.VALUE_SCALAR):
         _require_cuda()
         self.lib = _lib.load()
         c = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
@@ -214,9 +214,10 @@ class PairEngine:
         self.values = None
         self._host_values_sorted = None
         self._orig_values = None
-        self._vmin = self._vmax = 0.0
+        self._dz_bound = 0.0
+        self.nv, self.vmode = 1, _lib.VALUE_SCALAR
         if values is not None:
-            self.set_values(values)
+            self.set_values(values, value_mode)
         self.n_tiles = _lib.num_tiles(self.n)
         # interleaved tile shards: rank r sweeps tiles r, r+world, ... (balanced under culling)
         self.t0, self.t1, self.tstride = self.rank, self.n_tiles, self.world
@@ -256,18 +257,61 @@ class PairEngine:
             self._host_values_sorted = np.ascontiguousarray(self._orig_values[self.perm])
         return self._host_values_sorted
 
-    def set_values(self, values):
-        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).ravel()
-        if v.size != self.n:
-            raise ValueError("values length %d != number of points %d" % (v.size, self.n))
+    def set_values(self, values, value_mode=_lib.VALUE_SCALAR):
+        """values: (N,) observations, or (N, k) columns with value_mode VALUE_CROSS (k = 2,
+        |dz_0|*|dz_1|, Variogram.py:1979-1984) / VALUE_AGGREGATE (sqrt(sum dz_k^2), :1974-1977)."""
+        v = np.asarray(values, dtype=np.float64)
+        if v.ndim == 2 and value_mode == _lib.VALUE_SCALAR and v.shape[1] == 1:
+            v = v[:, 0]
+        if v.ndim == 1:
+            if value_mode != _lib.VALUE_SCALAR:
+                v = v[:, None]
+        elif v.ndim != 2 or value_mode == _lib.VALUE_SCALAR:
+            raise ValueError("values must be (N,) or (N, k) with a cross/aggregate value_mode")
+        if v.shape[0] != self.n:
+            raise ValueError("values length %d != number of points %d" % (v.shape[0], self.n))
+        if v.ndim == 2:
+            k = v.shape[1]
+            if (value_mode == _lib.VALUE_CROSS and k != 2) or not (1 <= k <= _lib.MAX_VALUE_COLUMNS):
+                raise ValueError("cross values need 2 columns, aggregate values 1..%d; got %d"
+                                 % (_lib.MAX_VALUE_COLUMNS, k))
+        v = np.ascontiguousarray(v)
         self._orig_values = v
-        self._values_unsorted = to_device(v, self.device)
+        self.nv = 1 if v.ndim == 1 else int(v.shape[1])
+        self.vmode = value_mode
+        cols = np.ascontiguousarray(v.T).reshape(self.nv, self.n)        # device layout [k][n]
+        dev = to_device(cols, self.device).view(self.nv, self.n)
+        self._values_unsorted = dev.reshape(-1)
         self.values = self._values_unsorted if self._perm_dev is None \
-            else self._values_unsorted[self._perm_dev].contiguous()
+            else dev[:, self._perm_dev].contiguous().view(-1)
         self._host_values_sorted = None
+        # upper bound of the per-pair difference, formed with the kernels' operand order so that
+        # monotone rounding keeps it >= every pair's value
         with np.errstate(invalid="ignore"):
-            self._vmin = float(np.nanmin(v)) if v.size else 0.0
-            self._vmax = float(np.nanmax(v)) if v.size else 0.0
+            rng = [float(abs(np.nanmax(c) - np.nanmin(c))) if c.size else 0.0 for c in cols]
+        rng = [r if r == r else 0.0 for r in rng]
+        if value_mode == _lib.VALUE_CROSS:
+            self._dz_bound = rng[0] * rng[1]
+        elif value_mode == _lib.VALUE_AGGREGATE:
+            acc = 0.0
+            for r in rng:
+                acc = acc + r * r
+            self._dz_bound = float(np.sqrt(acc))
+        else:
+            self._dz_bound = rng[0]
+
+    def _host_diff(self, i, j):
+        """Per-pair difference of host-resolved pairs (sorted indices), kernels' arithmetic."""
+        v = self._host_values
+        if self.vmode == _lib.VALUE_CROSS:
+            return np.abs(v[i, 0] - v[j, 0]) * np.abs(v[i, 1] - v[j, 1])
+        if self.vmode == _lib.VALUE_AGGREGATE:
+            acc = np.zeros(len(i))
+            for k in range(self.nv):
+                d = v[i, k] - v[j, k]
+                acc = acc + d * d
+            return np.sqrt(acc)
+        return np.abs(v[i] - v[j])
 
     def _buffer(self, name, numel, dtype):
         """Persistent device scratch (avoids allocator round trips on every call)."""
@@ -354,8 +398,7 @@ class PairEngine:
         dy = c[i, 1] - c[j, 1]
         s = dx * dx + dy * dy
         if self.values is not None:
-            v = self._host_values
-            dz = np.abs(v[i] - v[j])
+            dz = self._host_diff(i, j)
         else:
             dz = np.zeros(i.size)
         return np.ascontiguousarray(s).view(np.uint64), dz
@@ -374,7 +417,7 @@ class PairEngine:
         scratch = self._hist_scratch(nl)
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_hist(
-                _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), _hptr(thr),
+                _ptr(self.coords), _ptr(self.values), self.nv, self.vmode, self.n, self.dim, _hptr(dirp), _hptr(thr),
                 nl, int(stats), None, _ptr(cnt), _ptr(out[nl:2 * nl]), _ptr(out[2 * nl:]),
                 _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
@@ -395,6 +438,67 @@ class PairEngine:
         D.allreduce_sum_(out, self.group)  # the single collective of the fused pass
         host = to_host(out)
         return host[:nl].astype(np.int64), host[nl:2 * nl].copy(), host[2 * nl:].copy()
+
+    # -------------------------------------------------------- K2b (batched)
+    BATCH_CHUNK = 64  # value vectors uploaded per call
+
+    def hist_batch(self, edges, values, stat: int = _lib.STAT_SUM_SQ, dirp=None,
+                   thr_bits: Optional[np.ndarray] = None):
+        """Estimator sums of MANY value vectors over the same coordinates and lag edges:
+        values (K, N) -> (count int64[n_lags], sums float64[K, n_lags]) with
+        stat = STAT_SUM_SQ (sum dz^2) or STAT_SUM_SQRT (sum sqrt|dz|).  Four vectors share one
+        pair sweep (skg_pair_hist_batch); the engine's own values are left untouched."""
+        V = np.asarray(values, dtype=np.float64)
+        if V.ndim != 2 or V.shape[1] != self.n:
+            raise ValueError("values must be (K, %d); got %r" % (self.n, V.shape))
+        if stat not in (_lib.STAT_SUM_SQ, _lib.STAT_SUM_SQRT):
+            raise ValueError("stat must be STAT_SUM_SQ or STAT_SUM_SQRT")
+        thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        nl = int(thr.size)
+        K = int(V.shape[0])
+        if nl > self.lib.skg_pair_batch_max_lags():
+            raise ValueError("n_lags=%d exceeds the batched pass limit %d"
+                             % (nl, self.lib.skg_pair_batch_max_lags()))
+        amb = self.ambiguous_pairs(dirp)
+        sums = np.empty((K, nl))
+        counts = None
+        need = int(self.lib.skg_pair_batch_scratch_bytes(self.n, nl))
+        scratch = self._buffer("batch_scratch", need, torch.uint8)
+        for k0 in range(0, K, self.BATCH_CHUNK):
+            k1 = min(K, k0 + self.BATCH_CHUNK)
+            kb = k1 - k0
+            dev = to_device(V[k0:k1], self.device).view(kb, self.n)
+            if self._perm_dev is not None:
+                dev = dev[:, self._perm_dev].contiguous()
+            out = torch.zeros((kb + 1) * nl, dtype=torch.float64, device=self.device)
+            cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
+            with torch.cuda.device(self.device):
+                rc = self.lib.skg_pair_hist_batch(
+                    _ptr(self.coords), _ptr(dev), kb, self.n, self.dim, _hptr(dirp), _hptr(thr), nl,
+                    int(stat), _ptr(cnt), _ptr(out[nl:]), _ptr(scratch), scratch.numel(),
+                    self.t0, self.t1, self.tstride, self._stream())
+            _lib.check(rc, "skg_pair_hist_batch")
+            self.launches += (3 + 2 * ((kb + 3) // 4)) if self.t1 > self.t0 else 0
+            out[:nl] = cnt.to(torch.float64)
+            if amb is not None and amb[0].size:  # guard-band pairs, host-resolved
+                i, j = amb
+                s_bits, _ = self._amb_keys(amb)
+                g = np.searchsorted(thr, s_bits, side="right")
+                keep = g < nl
+                extra = np.zeros((kb + 1, nl))
+                np.add.at(extra[0], g[keep], 1.0)
+                perm = self.perm
+                for q in range(kb):
+                    vq = V[k0 + q][perm]
+                    dz = np.abs(vq[i] - vq[j])[keep]
+                    np.add.at(extra[1 + q], g[keep], dz * dz if stat == _lib.STAT_SUM_SQ else np.sqrt(dz))
+                out += to_device(extra.ravel(), self.device)
+            D.allreduce_sum_(out, self.group)
+            host = to_host(out).reshape(kb + 1, nl)
+            if counts is None:
+                counts = host[0].astype(np.int64)
+            sums[k0:k1] = host[1:]
+        return counts, sums
 
     # ------------------------------------------------ K1/K3 (order statistics)
     def _select_runner(self, key_kind, thr, dirp, n_buckets, collect_max=None):
@@ -427,7 +531,7 @@ class PairEngine:
             sc = np.ascontiguousarray(sc, dtype=np.float64)
             with torch.cuda.device(self.device):
                 rc = self.lib.skg_pair_select_hist(
-                    _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
+                    _ptr(self.coords), _ptr(self.values), self.nv, self.vmode, self.n, self.dim, _hptr(dirp),
                     _hptr(thr), nl, key_kind, _hptr(lo), _hptr(hi), _hptr(sc), n_buckets,
                     _ptr(hist), _ptr(mx) if (nl == 0 and collect_max is not None) else None,
                     _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
@@ -457,7 +561,7 @@ class PairEngine:
             sc = np.ascontiguousarray(sc, dtype=np.float64)
             with torch.cuda.device(self.device):
                 rc = self.lib.skg_pair_select_gather(
-                    _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp),
+                    _ptr(self.coords), _ptr(self.values), self.nv, self.vmode, self.n, self.dim, _hptr(dirp),
                     _hptr(thr), nl, key_kind, _hptr(lo), _hptr(hi), _hptr(sc), n_buckets,
                     _ptr(bm), _ptr(keys), _ptr(slots), _ptr(cnt), cap, _ptr(scratch),
                     scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
@@ -544,7 +648,7 @@ class PairEngine:
         vals = self.values if self.values is not None else self._buffer("zeros", self.n, torch.float64)
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_hist(
-                _ptr(self.coords), _ptr(vals), self.n, self.dim, _hptr(dirp), _hptr(thr), nl, 0,
+                _ptr(self.coords), _ptr(vals), 1, _lib.VALUE_SCALAR, self.n, self.dim, _hptr(dirp), _hptr(thr), nl, 0,
                 None, _ptr(cnt), None, None, _ptr(scratch), scratch.numel(), self.t0, self.t1,
                 self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
@@ -660,7 +764,7 @@ class PairEngine:
         sc = np.zeros(1, dtype=np.float64)
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_select_hist(
-                _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), None, 0,
+                _ptr(self.coords), _ptr(self.values), self.nv, self.vmode, self.n, self.dim, _hptr(dirp), None, 0,
                 _lib.KEY_SQDIST, _hptr(zero), _hptr(zero), _hptr(sc), 1, _ptr(hist), _ptr(mx),
                 _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_select_hist")
@@ -696,7 +800,7 @@ class PairEngine:
         dz_lo = np.ascontiguousarray(dz_lo, dtype=np.float64)
         with torch.cuda.device(self.device):
             rc = self.lib.skg_pair_hist(
-                _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(dirp), _hptr(thr), nl,
+                _ptr(self.coords), _ptr(self.values), self.nv, self.vmode, self.n, self.dim, _hptr(dirp), _hptr(thr), nl,
                 _lib.STAT_COUNT_BELOW, _hptr(dz_lo), _ptr(cnt), _ptr(below), None, _ptr(scratch),
                 scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
         _lib.check(rc, "skg_pair_hist")
@@ -729,7 +833,7 @@ class PairEngine:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
         nl = int(thr.size)
-        hi = to_bits(abs(self._vmax - self._vmin)) + 1  # fl(zmax - zmin) >= every |dz|
+        hi = to_bits(self._dz_bound) + 1  # >= every pair's difference
 
         def rank_fn(g, tot):
             return [] if tot == 0 else [(tot - 1) // 2, tot // 2]
@@ -790,7 +894,8 @@ class PairEngine:
         if m >= self.n:
             return None
         idx = np.sort(np.random.default_rng(12345).choice(self.n, size=m, replace=False))
-        sub = PairEngine(self._orig_coords[idx], self._orig_values[idx], device=self.device)
+        sub = PairEngine(self._orig_coords[idx], self._orig_values[idx], device=self.device,
+                         value_mode=self.vmode)
         q = self.WINDOW_HALF_QUANTILE
 
         def rank_fn(g, tot):
@@ -839,7 +944,7 @@ class PairEngine:
                 bufs["mask"] = torch.empty(m, dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 rc = self.lib.skg_pair_materialize(
-                    _ptr(self._coords_unsorted), _ptr(self._values_unsorted), self.n, self.dim,
+                    _ptr(self._coords_unsorted), _ptr(self._values_unsorted), self.nv, self.vmode, self.n, self.dim,
                     _hptr(dirp),
                     _hptr(thr), nl, _ptr(bufs.get("dist")), _ptr(bufs.get("diffs")),
                     _ptr(bufs.get("groups")), _ptr(bufs.get("mask")), k0, k1, self._stream())

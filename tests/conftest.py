@@ -58,3 +58,8 @@ def has_cuda():
 @pytest.fixture(scope="session")
 def golden_cv():
     return Golden("cross_validation")
+
+
+@pytest.fixture(scope="session")
+def golden_mv():
+    return Golden("multivariate")

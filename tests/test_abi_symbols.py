@@ -49,10 +49,10 @@ def test_tile_count_and_constants():
 def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     thr = np.array([1, 2, 3], dtype=np.uint64)
-    rc = lib.skg_pair_hist(None, None, 10, 2, None, thr.ctypes.data_as(C.c_void_p), 3, 1,
+    rc = lib.skg_pair_hist(None, None, 1, 0, 10, 2, None, thr.ctypes.data_as(C.c_void_p), 3, 1,
                            None, None, None, None, None, 0, 0, 0, 1, None)
     assert rc == -1 and b"NULL" in lib.skg_last_error()
-    rc = lib.skg_pair_materialize(C.c_void_p(8), None, 10, 5, None, None, 0, None, None, None,
+    rc = lib.skg_pair_materialize(C.c_void_p(8), None, 1, 0, 10, 5, None, None, 0, None, None, None,
                                   None, 0, 0, None)
     assert rc == -2 and b"dim" in lib.skg_last_error()
     rc = lib.skg_krige(None, None, 0, 2, None, None, None, None, 0, 0, None, 1.0, 1, 1, None, None,

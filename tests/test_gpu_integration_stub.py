@@ -21,7 +21,7 @@ def _bind():
     lib = C.CDLL(LIB)
     P, I64, I32 = C.c_void_p, C.c_int64, C.c_int
     lib.skg_pair_hist.restype = I32
-    lib.skg_pair_hist.argtypes = [P, P, I64, I32, P, P, I32, I32, P, P, P, P, P, I64, I64, I64, I64, P]
+    lib.skg_pair_hist.argtypes = [P, P, I32, I32, I64, I32, P, P, I32, I32, P, P, P, P, P, I64, I64, I64, I64, P]
     lib.skg_pair_scratch_bytes.restype = I64
     lib.skg_pair_scratch_bytes.argtypes = [I64, I32]
     lib.skg_pair_num_tiles.restype = I64
@@ -53,7 +53,7 @@ def _experimental_matheron(lib, coords, values, edges, sort):
     count = torch.zeros(len(edges), dtype=torch.int64, device="cuda")
     ssq = torch.zeros(len(edges), dtype=torch.float64, device="cuda")
     scratch = torch.empty(lib.skg_pair_scratch_bytes(n, len(edges)), dtype=torch.uint8, device="cuda")
-    rc = lib.skg_pair_hist(xy.data_ptr(), z.data_ptr(), n, dim, None, thr.ctypes.data, len(edges),
+    rc = lib.skg_pair_hist(xy.data_ptr(), z.data_ptr(), 1, 0, n, dim, None, thr.ctypes.data, len(edges),
                            1, None, count.data_ptr(), ssq.data_ptr(), None, scratch.data_ptr(),
                            scratch.numel(), 0, lib.skg_pair_num_tiles(n), 1, st)
     assert rc == 0, lib.skg_last_error()
@@ -84,10 +84,10 @@ def test_stub_rejects_bad_arguments_without_aborting():
     thr = np.array([5, 3], dtype=np.uint64)         # decreasing thresholds
     cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
     scratch = torch.empty(lib.skg_pair_scratch_bytes(8, 2), dtype=torch.uint8, device="cuda")
-    rc = lib.skg_pair_hist(xy.data_ptr(), z.data_ptr(), 8, 2, None, thr.ctypes.data, 2, 0, None,
+    rc = lib.skg_pair_hist(xy.data_ptr(), z.data_ptr(), 1, 0, 8, 2, None, thr.ctypes.data, 2, 0, None,
                            cnt.data_ptr(), None, None, scratch.data_ptr(), scratch.numel(), 0, 1, 1, None)
     assert rc < 0
     assert b"non-decreasing" in lib.skg_last_error()
-    rc = lib.skg_pair_hist(xy.data_ptr(), z.data_ptr(), 8, 5, None, thr.ctypes.data, 0, 0, None,
+    rc = lib.skg_pair_hist(xy.data_ptr(), z.data_ptr(), 1, 0, 8, 5, None, thr.ctypes.data, 0, 0, None,
                            cnt.data_ptr(), None, None, scratch.data_ptr(), scratch.numel(), 0, 1, 1, None)
     assert rc < 0
