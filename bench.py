@@ -233,7 +233,9 @@ def run_own(args):
     h2d, d2h = Traffic.h2d // e2e_steps, Traffic.d2h // e2e_steps
     assert np.allclose(exp, V.experimental, rtol=1e-12)
     krig = None
+    batched = None
     if world == 1 and not args.no_kriging:
+        batched = bench_batched(skg, V, c, v)
         krig = bench_kriging(skg, args)  # sampled too: the longest loaded stretch of the run
     clocks = sampler.stop()
 
@@ -297,10 +299,39 @@ def run_own(args):
                                          "%.1f s" % (sp, dt)}
         if krig is not None:
             out["kriging"] = krig
+        if batched is not None:
+            out["batched"] = batched
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_batched(skg, V, c, v, k=32):
+    """k value vectors over the same coordinates and bins (Monte-Carlo
+    propagation) through the batched pair sweep, next to one fused pass per vector."""
+    import torch
+    rng = np.random.default_rng(1)
+    draws = np.vstack([v + rng.normal(0.0, 0.05 * np.std(v), v.size) for _ in range(k)])
+    pairs = v.size * (v.size - 1) // 2
+    V.experimental_batch(draws[:4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = V.experimental_batch(draws)
+    torch.cuda.synchronize()
+    tb = time.perf_counter() - t0
+    edges = V.bins
+    t0 = time.perf_counter()
+    for q in range(k):
+        one = skg.Variogram(V._X, draws[q], n_lags=len(edges), maxlag=V.maxlag, fit_method=None).experimental
+    torch.cuda.synchronize()
+    ts = time.perf_counter() - t0
+    assert np.allclose(got[-1], one, rtol=1e-12)
+    V.experimental  # leaves the engine's values as they were
+    return {"metric": "vector-pairs/s", "vectors": k, "e2e": {"value": k * pairs / tb, "unit": "vector-pairs/s",
+            "ms": tb * 1e3, "call": "Variogram.experimental_batch(values[%d, N])" % k},
+            "per_vector_e2e": {"value": k * pairs / ts, "unit": "vector-pairs/s", "ms": ts * 1e3,
+                               "call": "Variogram(MetricSpace, values_k).experimental x %d" % k}}
 
 
 def bench_kriging(skg, args):

@@ -546,8 +546,9 @@ static double bits_to_double(uint64_t b) {
 }
 
 static size_t hist_smem_bytes(int nb, int stats, bool priv) {
-  const size_t S = priv ? HB : 1;
-  return (size_t)nb * S * (stats == 3 ? 32 : 16);
+  if (!priv) return (size_t)nb * (stats == 3 ? 32 : 16);
+  const int sumb = stats == 3 ? 16 : (stats == 4 ? 4 : (stats == 0 ? 0 : 8));
+  return ((size_t)nb * HB * (sumb + 4) + 15) & ~(size_t)15;
 }
 
 template <int DIM, int DIR, int EMAX, bool PRIV>

@@ -95,6 +95,8 @@ __device__ __forceinline__ void chunk_box(const double* __restrict__ bbox32, int
 // compiler knows accumulator stores cannot alias table/tile loads and is free to
 // hoist the next pairs' loads and fp64 math above them.
 
+constexpr int HB_THREADS = 64;  // threads per CTA of the fused / select sweeps (= HB)
+
 struct DzTable {  // per-lag |dz| thresholds of the below-count mode (STATS == 4)
   double lo[THR_MAX];
 };
@@ -114,66 +116,80 @@ struct HistPartial {  // one per (CTA, lag class)
 struct HistRec16 { double sum; unsigned long long cnt; };
 struct HistRec32 { double sq; unsigned long long cnt; double rt; unsigned long long pad; };
 
+// Private per-thread accumulators, split layout (PRIV): sums[lag][thread] for all lag classes,
+// then u32 counts[lag][thread], so a warp's read-modify-write of one lag moves 8+4 bytes per
+// lane instead of a padded 16-byte record (shared-memory wavefronts are what bounds the sweep).  sum part per thread: STATS 1/2 one
+// double, 3 two doubles {sum_sq, sum_sqrt}, 4 one u32 (below-count), 0 nothing.
 template <int STATS>
-__device__ __forceinline__ void rmw_record(unsigned addr, double dz, int pred) {
+struct PrivLayout {
+  static constexpr int SUMB = STATS == 3 ? 16 : (STATS == 4 ? 4 : (STATS == 0 ? 0 : 8));
+  static constexpr int LAGB = HB_THREADS * (SUMB + 4);  // bytes per lag class in total
+};
+
+template <int STATS>
+__device__ __forceinline__ void rmw_split(unsigned saddr, unsigned caddr, double dz, int pred) {
   if (STATS == 3) {
     const double rt = sqrt(fabs(dz));
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 tb, cb, rb, pb;\n\t.reg .f64 t, u;\n\t"
-        "setp.ne.s32 p, %3, 0;\n\t"
-        "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
-        "@p ld.shared.v2.b64 {rb, pb}, [%0+16];\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 tb, rb;\n\t.reg .f64 t, u;\n\t.reg .b32 c;\n\t"
+        "setp.ne.s32 p, %4, 0;\n\t"
+        "@p ld.shared.v2.b64 {tb, rb}, [%0];\n\t"
+        "@p ld.shared.u32 c, [%1];\n\t"
         "mov.b64 t, tb;\n\tmov.b64 u, rb;\n\t"
-        "fma.rn.f64 t, %1, %1, t;\n\t"
-        "add.rn.f64 u, u, %2;\n\t"
-        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
+        "fma.rn.f64 t, %2, %2, t;\n\t"
+        "add.rn.f64 u, u, %3;\n\t"
+        "add.u32 c, c, 1;\n\t"
         "mov.b64 tb, t;\n\tmov.b64 rb, u;\n\t"
-        "@p st.shared.v2.b64 [%0], {tb, cb};\n\t"
-        "@p st.shared.b64 [%0+16], rb;\n\t}"
-        :: "r"(addr), "d"(dz), "d"(rt), "r"(pred));
+        "@p st.shared.v2.b64 [%0], {tb, rb};\n\t"
+        "@p st.shared.u32 [%1], c;\n\t}"
+        :: "r"(saddr), "r"(caddr), "d"(dz), "d"(rt), "r"(pred));
   } else if (STATS == 2) {
     const double rt = sqrt(fabs(dz));
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 tb, cb;\n\t.reg .f64 t;\n\t"
-        "setp.ne.s32 p, %2, 0;\n\t"
-        "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 tb;\n\t.reg .f64 t;\n\t.reg .b32 c;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t"
+        "@p ld.shared.b64 tb, [%0];\n\t"
+        "@p ld.shared.u32 c, [%1];\n\t"
         "mov.b64 t, tb;\n\t"
-        "add.rn.f64 t, t, %1;\n\t"
-        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
+        "add.rn.f64 t, t, %2;\n\t"
+        "add.u32 c, c, 1;\n\t"
         "mov.b64 tb, t;\n\t"
-        "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
-        :: "r"(addr), "d"(rt), "r"(pred));
+        "@p st.shared.b64 [%0], tb;\n\t"
+        "@p st.shared.u32 [%1], c;\n\t}"
+        :: "r"(saddr), "r"(caddr), "d"(rt), "r"(pred));
   } else if (STATS == 1) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 tb, cb;\n\t.reg .f64 t;\n\t"
-        "setp.ne.s32 p, %2, 0;\n\t"
-        "@p ld.shared.v2.b64 {tb, cb}, [%0];\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 tb;\n\t.reg .f64 t;\n\t.reg .b32 c;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t"
+        "@p ld.shared.b64 tb, [%0];\n\t"
+        "@p ld.shared.u32 c, [%1];\n\t"
         "mov.b64 t, tb;\n\t"
-        "fma.rn.f64 t, %1, %1, t;\n\t"
-        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
+        "fma.rn.f64 t, %2, %2, t;\n\t"
+        "add.u32 c, c, 1;\n\t"
         "mov.b64 tb, t;\n\t"
-        "@p st.shared.v2.b64 [%0], {tb, cb};\n\t}"
-        :: "r"(addr), "d"(dz), "r"(pred));
+        "@p st.shared.b64 [%0], tb;\n\t"
+        "@p st.shared.u32 [%1], c;\n\t}"
+        :: "r"(saddr), "r"(caddr), "d"(dz), "r"(pred));
   } else if (STATS == 4) {
-    // dz carries the 0/1 "below the per-lag |dz| threshold" flag: low word of the first
-    // 8 bytes counts those pairs, low word of the second 8 bytes counts all pairs
+    // dz carries the 0/1 "below the per-lag |dz| threshold" flag
     const int below = dz != 0.0 ? 1 : 0;
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 bb, cb;\n\t.reg .b32 lo, hi;\n\t"
-        "setp.ne.s32 p, %2, 0;\n\t"
-        "@p ld.shared.v2.b64 {bb, cb}, [%0];\n\t"
-        "mov.b64 {lo, hi}, bb;\n\tadd.u32 lo, lo, %1;\n\tmov.b64 bb, {lo, hi};\n\t"
-        "mov.b64 {lo, hi}, cb;\n\tadd.u32 lo, lo, 1;\n\tmov.b64 cb, {lo, hi};\n\t"
-        "@p st.shared.v2.b64 [%0], {bb, cb};\n\t}"
-        :: "r"(addr), "r"(below), "r"(pred));
+        "{\n\t.reg .pred p;\n\t.reg .b32 b, c;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t"
+        "@p ld.shared.u32 b, [%0];\n\t"
+        "@p ld.shared.u32 c, [%1];\n\t"
+        "add.u32 b, b, %2;\n\tadd.u32 c, c, 1;\n\t"
+        "@p st.shared.u32 [%0], b;\n\t"
+        "@p st.shared.u32 [%1], c;\n\t}"
+        :: "r"(saddr), "r"(caddr), "r"(below), "r"(pred));
   } else {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 cb;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b32 c;\n\t"
         "setp.ne.s32 p, %1, 0;\n\t"
-        "@p ld.shared.b64 cb, [%0+8];\n\t"
-        "{ .reg .b32 lo, hi; mov.b64 {lo, hi}, cb; add.u32 lo, lo, 1; mov.b64 cb, {lo, hi}; }\n\t"
-        "@p st.shared.b64 [%0+8], cb;\n\t}"
-        :: "r"(addr), "r"(pred));
+        "@p ld.shared.u32 c, [%0];\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "@p st.shared.u32 [%0], c;\n\t}"
+        :: "r"(caddr), "r"(pred));
   }
 }
 
@@ -202,7 +218,7 @@ __device__ __forceinline__ double mv_diff(const double* __restrict__ mvI, const 
   return sqrt(acc);
 }
 
-constexpr int HB = 64;          // threads per CTA
+constexpr int HB = HB_THREADS;   // threads per CTA
 constexpr int HR = TILE / HB;   // i-points per thread
 
 template <int EMAX>
@@ -225,6 +241,29 @@ __device__ __forceinline__ int lag_of(uint64_t sb, const uint64_t* sThr, const u
   return g;
 }
 
+// Lag class times 8 (= byte offset of the lag's threshold), straight from a u16 LUT that
+// stores lut[cell] * 8: the threshold load needs no index scaling, and both accumulator
+// addresses are one multiply-add each from the result (thread base folded in).
+template <int EMAX>
+__device__ __forceinline__ unsigned lag_off8(uint64_t sb, const uint64_t* sThr,
+                                             const unsigned char* lutBytesBiased, int shift,
+                                             int klo, int khi, int emax) {
+  // lutBytesBiased = (bytes of the u16 LUT) - 2 * klo
+  const int k = (int)((uint32_t)(sb >> 32) >> shift);
+  unsigned g8 = *reinterpret_cast<const uint16_t*>(lutBytesBiased + 2 * min(max(k, klo), khi));
+  const double s = __longlong_as_double((long long)sb);
+  const char* thrBytes = reinterpret_cast<const char*>(sThr);
+  if (EMAX > 0) {
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e)
+      g8 += (s >= *reinterpret_cast<const double*>(thrBytes + g8)) ? 8u : 0u;
+  } else {
+    for (int e = 0; e < emax; ++e)
+      g8 += (s >= *reinterpret_cast<const double*>(thrBytes + g8)) ? 8u : 0u;
+  }
+  return g8;
+}
+
 // PRIV: private per-thread records + software-pipelined loop (front end of pair set
 // jj+1 is issued before the read-modify-writes of pair set jj).
 // !PRIV (n_lags too large for private records): one shared record per lag + atomics.
@@ -240,32 +279,37 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
   __shared__ uint64_t sThr[THR_MAX];
-  __shared__ uint8_t sLut[LUT_MAX];
+  __shared__ uint16_t sLut[LUT_MAX];  // lut[cell] * 8
   __shared__ double sDzLo[STATS == 4 ? THR_MAX : 1];  // per-lag |dz| thresholds (below-count mode)
   extern __shared__ __align__(16) unsigned char acc_raw[];
 
-  constexpr int REC = (STATS == 3) ? 32 : 16;
+  constexpr int REC = (STATS == 3) ? 32 : 16;              // shared records of the !PRIV path
+  using PL = PrivLayout<STATS>;
+  constexpr int LAGB = PRIV ? PL::LAGB : REC;               // bytes per lag class
   const int nb = tab.nb;
-  const int S = PRIV ? HB : 1;
   const int tid = threadIdx.x;
   const double qnan = __longlong_as_double(NAN_BITS);
 
   for (int k = tid; k < THR_MAX; k += HB) sThr[k] = tab.thr[k];
-  for (int k = tid; k < tab.ncell; k += HB) sLut[k] = tab.lut[k];
+  for (int k = tid; k < tab.ncell; k += HB) sLut[k] = (uint16_t)(tab.lut[k] * 8);
   if (STATS == 4) {
     for (int k = tid; k < THR_MAX; k += HB) sDzLo[k] = k < nb ? dzt.lo[k] : 0.0;
   }
   {
     unsigned long long* z = reinterpret_cast<unsigned long long*>(acc_raw);
-    for (int k = tid; k < nb * S * (REC / 8); k += HB) z[k] = 0ull;
+    for (int k = tid; k < nb * (LAGB / 8); k += HB) z[k] = 0ull;
   }
   __syncthreads();
 
   const int shift = tab.shift, klo = tab.key0, khi = tab.key0 + tab.ncell - 1, emax = tab.emax;
-  const uint8_t* lutb = sLut - klo;
-  const unsigned aRec = (unsigned)__cvta_generic_to_shared(acc_raw) + (PRIV ? tid * REC : 0);
+  const unsigned char* lutb = reinterpret_cast<const unsigned char*>(sLut) - 2 * klo;
+  constexpr int GS = 8;  // lag ids are carried times 8 (threshold byte offsets)
+  const unsigned nbS = (unsigned)nb * GS;
+  const unsigned aBase = (unsigned)__cvta_generic_to_shared(acc_raw);
+  const unsigned aSum = aBase + tid * PL::SUMB;
+  const unsigned aCnt = aBase + (unsigned)nb * (HB * PL::SUMB) + tid * 4;  // counts behind all sums
   // multi-column values: both tiles' columns behind the records
-  double* mvI = reinterpret_cast<double*>(acc_raw + (size_t)nb * S * REC);
+  double* mvI = reinterpret_cast<double*>(acc_raw + (size_t)nb * LAGB);
   double* mvJ = mvI + (VM ? mv.nv * TILE : 0);
   const int64_t nt = (n + TILE - 1) / TILE;
   const double* __restrict__ X = coords;
@@ -332,7 +376,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
     auto body = [&](auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
       // front end of pair set jj: lag classes g[] (nb = not accumulated) and dz[]
-      auto front = [&](int jj, int (&g)[HR], double (&dz)[HR]) {
+      auto front = [&](int jj, unsigned (&g)[HR], double (&dz)[HR]) {
         const double2 pj = sXY[jj];
         const double zj = sZ[jj];
         const double wj = (DIM == 3) ? sW[jj] : 0.0;
@@ -346,24 +390,25 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
             s = __dadd_rn(s, __dmul_rn(dw, dw));
           }
           const uint64_t sb = (uint64_t)__double_as_longlong(s);
-          int gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
-          if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
+          unsigned gg = lag_off8<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
+          if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nbS : gg;  // keep i < j only
           if (DIR) {
-            if (gg < nb && !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nb;
+            if (gg < nbS && !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nbS;
           }
           g[r] = gg;
           dz[r] = VM ? mv_diff(mvI, mvJ, r * HB + tid, jj, mv) : zi[r] - zj;
-          if (STATS == 4) dz[r] = (fabs(dz[r]) < sDzLo[min(gg, nb - 1)]) ? 1.0 : 0.0;
+          if (STATS == 4) dz[r] = (fabs(dz[r]) < sDzLo[min(gg, nbS - GS) / GS]) ? 1.0 : 0.0;
         }
       };
-      auto accumulate = [&](const int (&g)[HR], const double (&dz)[HR]) {
+      auto accumulate = [&](const unsigned (&g)[HR], const double (&dz)[HR]) {
 #pragma unroll
         for (int r = 0; r < HR; ++r) {
-          const int in = g[r] < nb ? 1 : 0;
+          const int in = g[r] < nbS ? 1 : 0;
           if (PRIV) {
-            rmw_record<STATS>(aRec + (unsigned)g[r] * (unsigned)(HB * REC), dz[r], in);
+            rmw_split<STATS>(aSum + g[r] * (unsigned)(PL::SUMB * HB / 8), aCnt + g[r] * (unsigned)(HB * 4 / 8),
+                             dz[r], in);
           } else if (in) {
-            unsigned char* rec = acc_raw + g[r] * REC;
+            unsigned char* rec = acc_raw + (g[r] / GS) * REC;
             atomicAdd(reinterpret_cast<unsigned long long*>(rec + 8), 1ull);
             if (STATS & SKG_STAT_SUM_SQ) atomicAdd(reinterpret_cast<double*>(rec), dz[r] * dz[r]);
             if (STATS & SKG_STAT_SUM_SQRT)
@@ -371,7 +416,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
           }
         }
       };
-      int gA[HR], gB[HR];
+      unsigned gA[HR], gB[HR];
       double dA[HR], dB[HR];
       front(0, gA, dA);
       int jj = 1;
@@ -399,11 +444,14 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
       double a = 0.0, b = 0.0;
 #pragma unroll
       for (int k = 0; k < HB / 32; ++k) {
-        const unsigned char* rec = acc_raw + (size_t)(gI * HB + lane + 32 * k) * REC;
-        c += *reinterpret_cast<const unsigned int*>(rec + 8);  // per-thread counts stay < 2^32
-        if (STATS == 4) a += (double)*reinterpret_cast<const unsigned int*>(rec);
-        else if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(rec);
-        if (STATS & SKG_STAT_SUM_SQRT) b += *reinterpret_cast<const double*>(rec + (STATS == 3 ? 16 : 0));
+        const int th = lane + 32 * k;
+        const unsigned char* sp = acc_raw + (size_t)(gI * HB + th) * PL::SUMB;
+        c += *reinterpret_cast<const unsigned int*>(acc_raw + (size_t)nb * (HB * PL::SUMB) +
+                                                    (size_t)(gI * HB + th) * 4);  // counts < 2^32
+        if (STATS == 4) a += (double)*reinterpret_cast<const unsigned int*>(sp);
+        else if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(sp);
+        if (STATS == 2) b += *reinterpret_cast<const double*>(sp);
+        if (STATS == 3) b += *reinterpret_cast<const double*>(sp + 8);
       }
       c = warp_sum(c);
       if ((STATS & SKG_STAT_SUM_SQ) || STATS == 4) a = warp_sum(a);

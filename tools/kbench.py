@@ -33,7 +33,7 @@ for n in sizes:
     for i in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = lib.skg_pair_hist(_ptr(eng.coords), _ptr(eng.values), eng.n, eng.dim, None, _hptr(thr),
+        rc = lib.skg_pair_hist(_ptr(eng.coords), _ptr(eng.values), 1, 0, eng.n, eng.dim, None, _hptr(thr),
                                nl, stats, None, _ptr(cnt), _ptr(sq), _ptr(rt), _ptr(scratch),
                                scratch.numel(), 0, eng.n_tiles, 1, eng._stream())
         e1.record()
