@@ -205,7 +205,7 @@ def run_own(args):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = lib.skg_pair_hist(_ptr(eng.coords), _ptr(eng.values), eng.n, eng.dim, None, _hptr(thr),
+        rc = lib.skg_pair_hist(_ptr(eng.coords), _ptr(eng.values), 1, 0, eng.n, eng.dim, None, _hptr(thr),
                                nl, _lib.STAT_SUM_SQ, None, _ptr(cnt_d), _ptr(sq_d), None, _ptr(scratch),
                                scratch.numel(), eng.t0, eng.t1, eng.tstride, eng._stream())
         e1.record()

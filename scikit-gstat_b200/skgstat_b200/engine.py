@@ -108,72 +108,6 @@ def literal_mask(dx, dy, dirp):
     return ok
 
 
-def morton_order(c: np.ndarray) -> np.ndarray:
-    """Permutation that sorts points along a Z-order curve over their bounding box.
-
-    The pair kernels give each lane of a warp one "i" point; with spatially sorted
-    points the lanes of a warp are neighbours, so for a given "j" point they fall into
-    the same or adjacent lag classes: the lag-table reads broadcast, the per-lag
-    accumulator traffic is skipped for whole warps outside maxlag.  Results do not
-    depend on the order (counts exactly, sums to rounding)."""
-    ct = np.ascontiguousarray(c.T)  # contiguous per-dimension rows: fast reductions
-    dim, n = ct.shape
-    bits = 21 if dim == 3 else 31
-    u = np.uint64
-    key = np.zeros(n, dtype=np.uint64)
-    for k in range(dim):
-        row = ct[k]
-        lo = np.nanmin(row) if n else 0.0
-        ext = (np.nanmax(row) - lo) if n else 1.0
-        if not (ext > 0):
-            ext = 1.0
-        with np.errstate(invalid="ignore"):
-            q = ((row - lo) * ((2 ** bits - 1) / ext)).astype(np.int64)  # NaN -> arbitrary cell
-        v = np.clip(q, 0, 2 ** bits - 1).astype(np.uint64)
-        if dim == 2:  # spread 32 bits to even positions
-            v = (v | (v << u(16))) & u(0x0000FFFF0000FFFF)
-            v = (v | (v << u(8))) & u(0x00FF00FF00FF00FF)
-            v = (v | (v << u(4))) & u(0x0F0F0F0F0F0F0F0F)
-            v = (v | (v << u(2))) & u(0x3333333333333333)
-            v = (v | (v << u(1))) & u(0x5555555555555555)
-        else:  # spread 21 bits to every third position
-            v = (v | (v << u(32))) & u(0x1F00000000FFFF)
-            v = (v | (v << u(16))) & u(0x1F0000FF0000FF)
-            v = (v | (v << u(8))) & u(0x100F00F00F00F00F)
-            v = (v | (v << u(4))) & u(0x10C30C30C30C30C3)
-            v = (v | (v << u(2))) & u(0x1249249249249249)
-        key |= v << u(k)
-    return np.argsort(key)
-
-
-def morton_order_device(ct: torch.Tensor) -> torch.Tensor:
-    """Z-order permutation computed on the device (ct: (dim, N) fp64 CUDA tensor).  Input
-    layout plumbing only (a few elementwise torch ops and one sort); the host version
-    `morton_order` produces the same kind of ordering and is used by the CPU tests."""
-    dim, n = ct.shape
-    bits = 21 if dim == 3 else 31
-    key = torch.zeros(n, dtype=torch.int64, device=ct.device)
-    for k in range(dim):
-        row = torch.nan_to_num(ct[k], nan=0.0, posinf=0.0, neginf=0.0)
-        lo = row.min()
-        ext = torch.clamp(row.max() - lo, min=1e-300)
-        v = ((row - lo) * ((2 ** bits - 1) / ext)).to(torch.int64).clamp_(0, 2 ** bits - 1)
-        if dim == 2:
-            v = (v | (v << 16)) & 0x0000FFFF0000FFFF
-            v = (v | (v << 8)) & 0x00FF00FF00FF00FF
-            v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0F
-            v = (v | (v << 2)) & 0x3333333333333333
-            v = (v | (v << 1)) & 0x5555555555555555
-        else:
-            v = (v | (v << 32)) & 0x1F00000000FFFF
-            v = (v | (v << 16)) & 0x1F0000FF0000FF
-            v = (v | (v << 8)) & 0x100F00F00F00F00F
-            v = (v | (v << 4)) & 0x10C30C30C30C30C3
-            v = (v | (v << 2)) & 0x1249249249249249
-        key |= v << k
-    return torch.argsort(key, stable=True)
-
-
 class PairEngine:
     """Pair sweeps over one point set resident in HBM (SoA fp64)."""
 
