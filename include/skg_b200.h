@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SKG_ABI_VERSION 2
+#define SKG_ABI_VERSION 3
 #define SKG_TILE 256            /* points per tile edge                          */
 #define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
 #define SKG_KRIGE_MAX_POINTS 64 /* max_points supported by the warp-per-target kernel */
@@ -84,6 +84,7 @@ extern "C" {
 #define SKG_MODEL_GAUSSIAN 2    /* models.py:147-209 */
 #define SKG_MODEL_CUBIC 3       /* models.py:212-272 */
 #define SKG_MODEL_STABLE 4      /* models.py:275-344 */
+#define SKG_MODEL_MATERN 5      /* models.py:347-422 (K_nu evaluated on the device) */
 
 /* kriging per-target status (Kriging.py:25-38, 492-513) */
 #define SKG_KRIGE_OK 0
@@ -254,8 +255,13 @@ int skg_krige_build_grid(const double* coords, int64_t n, int dim, const double*
  * border 1, corner 0; b_i = gamma(d_0i), b_n = 1 (Kriging.py:594-614); solved
  * by partial-pivot LU in fp64; sigma = sum(w_i b_i) + lambda, z = w . values
  * (Kriging.py:644-647).
- *   model_params [host, 4 doubles]: range r, sill c0, shape s (stable only),
- *                nugget b (0 = none) - the cof of Variogram.fitted_model_function
+ *   model_params [host, 6 doubles]: range r, sill c0, shape/smoothness s (stable, matern),
+ *                nugget b (0 = none) - the cof of Variogram.fitted_model_function -,
+ *                then the table range and the beyond-table value of matrix_lut
+ *   matrix_lut [dev, lut_size] or NULL: OrdinaryKriging(mode='estimate') (Kriging.py:656-679) -
+ *                the kriging MATRIX takes gamma from this table, index
+ *                int((d / model_params[4]) * lut_size), model_params[5] beyond it; the
+ *                right-hand side always uses the exact model (Kriging.py:611-613)
  *   targets [dev, dim*m] SoA; z, sigma [dev, m] (out); status [dev, m] int32 (out)
  *   scratch [dev] >= skg_krige_scratch_bytes(max_points) bytes
  *   [target_begin, target_end) sub-range (multi-GPU sharding; outputs indexed
@@ -272,6 +278,7 @@ int64_t skg_krige_scratch_bytes(int max_points);
 int skg_krige(const double* coords, const double* values, int64_t n, int dim,
               const double* grid, const int32_t* cell_start, const int32_t* order,
               const double* targets, int64_t m, int model, const double* model_params,
+              const double* matrix_lut, int lut_size,
               double radius, int min_points, int max_points, const int32_t* exclude,
               double* z, double* sigma, int32_t* status,
               void* scratch, int64_t scratch_bytes,

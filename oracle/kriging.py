@@ -53,8 +53,19 @@ def stable(h, r, c0, s, b=0.0):
     return np.where(h == 0, b, v)
 
 
+def matern(h, r, c0, s, b=0.0):
+    """models.py:413-422 (h == 0 -> b; scipy.special.kv / gamma)."""
+    from scipy import special
+    h = np.asarray(h, dtype=float)
+    a = r / 2.0
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        v = b + c0 * (1.0 - (2 / special.gamma(s)) * np.power((h * np.sqrt(s)) / a, s)
+                      * special.kv(s, 2 * ((h * np.sqrt(s)) / a)))
+    return np.where(h == 0, b, v)
+
+
 MODELS = dict(spherical=spherical, exponential=exponential, gaussian=gaussian,
-              cubic=cubic, stable=stable)
+              cubic=cubic, stable=stable, matern=matern)
 
 
 def fitted_model(model, effective_range, sill, nugget=0.0, shape=None):
@@ -85,8 +96,21 @@ def find_closest(dist_row, max_dist, n):
     return ridx
 
 
+def estimate_matrix(dist, gamma, effective_range, sill, precision):
+    """Kriging.py:656-679 (mode='estimate'): semivariances of the kriging matrix from a table
+    of `precision` values over [0, range]; beyond the table the sill."""
+    prec_g = gamma(np.linspace(0, effective_range, precision))
+    dist_n = ((dist / effective_range) * precision).astype(int)
+    g = np.ones(dist_n.shape) * -1
+    out_ = np.where(dist_n >= precision)[0]
+    in_ = np.where(dist_n < precision)[0]
+    g[out_] = sill
+    g[in_] = prec_g[dist_n[in_]]
+    return g
+
+
 def krige(coords, values, targets, model, effective_range, sill, nugget=0.0,
-          shape=None, min_points=5, max_points=15, chunk=2048):
+          shape=None, min_points=5, max_points=15, chunk=2048, mode="exact", precision=100):
     """Kriging.py:405-650.  Returns (z, sigma, status) with status 0 = ok,
     1 = fewer than min_points neighbours (LessPointsError -> NaN),
     2 = singular matrix (numpy LinAlgError; the reference would let that
@@ -114,7 +138,10 @@ def krige(coords, values, targets, model, effective_range, sill, nugget=0.0,
             # MetricSpace.py:158-187: sub-matrix of the cached pdist matrix
             dist_mat = pdist(in_range, metric="euclidean")
             n = len(in_range)
-            a = squareform(gamma(dist_mat))                  # Kriging.py:594-600
+            if mode == "exact":                              # Kriging.py:594-600
+                a = squareform(gamma(dist_mat))
+            else:
+                a = squareform(estimate_matrix(dist_mat, gamma, effective_range, sill, precision))
             a = np.concatenate((a, np.ones((n, 1))), axis=1)
             a = np.concatenate((a, np.ones((1, n + 1))), axis=0)
             a[-1, -1] = 0

@@ -320,6 +320,67 @@ def make_multivariate(skg, ds):
     print("multivariate cases:", len(manifest))
 
 
+def make_kriging_ext(skg, ds):
+    """SURVEY.md 8(f) N2 leftovers: Matern model (models.py:347-422) and
+    OrdinaryKriging(mode='estimate') (Kriging.py:343-352, 656-679)."""
+    arrays, manifest = {}, []
+    rng = np.random.default_rng(17)
+    c = random_points(1000, 500.0, 2, seed=5)
+    v = gaussian_field(c, 60.0, seed=5)
+    arrays["in/rnd1000/coords"] = c
+    arrays["in/rnd1000/values"] = v
+    lo, hi = c.min(axis=0), c.max(axis=0)
+    t = lo + rng.random((250, 2)) * (hi - lo)
+    t = np.vstack((t, c[:10]))
+    arrays["targets"] = t
+    cases = [
+        dict(model="matern", mode="exact", max_points=16, manual=dict(fit_range=180.0, fit_sill=3.4, fit_shape=0.7)),
+        dict(model="matern", mode="exact", max_points=24, manual=dict(fit_range=200.0, fit_sill=3.4, fit_shape=1.5)),
+        dict(model="matern", mode="exact", max_points=12, manual=dict(fit_range=150.0, fit_sill=3.0, fit_shape=2.4),
+             use_nugget=True, nugget=0.2),
+        dict(model="exponential", mode="estimate", precision=100, max_points=20),
+        dict(model="spherical", mode="estimate", precision=800, max_points=15),
+        dict(model="exponential", mode="estimate", precision=1000, max_points=32, use_nugget=True),
+        dict(model="matern", mode="estimate", precision=200, max_points=16,
+             manual=dict(fit_range=180.0, fit_sill=3.4, fit_shape=0.7)),
+    ]
+    for case in cases:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            extra = {}
+            if "manual" in case:
+                extra = dict(fit_method="manual", **case["manual"])
+                if "nugget" in case:
+                    extra["fit_nugget"] = case["nugget"]
+            V = skg.Variogram(c, v, model=case["model"], n_lags=20, maxlag="median",
+                              use_nugget=case.get("use_nugget", False), **extra)
+            ok = skg.OrdinaryKriging(V, min_points=4, max_points=case["max_points"], mode=case["mode"],
+                                     precision=case.get("precision", 100))
+            z = ok.transform(t[:, 0], t[:, 1])
+        d = V.describe()
+        key = "e/%d" % len(manifest)
+        arrays[key + "/z"] = z
+        arrays[key + "/sigma"] = ok.sigma
+        entry = dict(case)
+        entry.update(key=key, effective_range=float(d["effective_range"]), sill=float(d["sill"]),
+                     nugget=float(d["nugget"]),
+                     shape=(float(d["smoothness"]) if "smoothness" in d else
+                            (float(d["shape"]) if "shape" in d else None)),
+                     no_points_error=int(ok.no_points_error), singular_error=int(ok.singular_error))
+        manifest.append(entry)
+        print(key, case["model"], case["mode"], "nan:", int(np.isnan(z).sum()), "of", len(z))
+    # the Matern semivariance itself on a grid of (h, smoothness): pins the device Bessel function
+    from skgstat import models as rm
+    hs = np.concatenate(([0.0], np.geomspace(1e-3, 900.0, 120)))
+    for k, sm in enumerate((0.2, 0.5, 0.7, 1.0, 1.5, 2.4, 3.0, 5.5, 10.0, 19.5)):
+        arrays["matern/%d" % k] = np.array([rm.matern.py_func(h, 200.0, 3.0, sm, 0.1) if hasattr(rm.matern, "py_func")
+                                            else rm.matern(np.array([h]), 200.0, 3.0, sm, 0.1)[0] for h in hs])
+    arrays["matern/h"] = hs
+    arrays["matern/s"] = np.array((0.2, 0.5, 0.7, 1.0, 1.5, 2.4, 3.0, 5.5, 10.0, 19.5))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "kriging_ext.npz"), **arrays)
+
+
 def make_api_fixture(skg):
     """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
     test_variogram.py::test_fit_lm; data only."""
@@ -333,7 +394,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -346,6 +407,8 @@ def main():
         make_api_fixture(skg)
     if "multivariate" in which:
         make_multivariate(skg, ds)
+    if "kriging_ext" in which:
+        make_kriging_ext(skg, ds)
 
 
 if __name__ == "__main__":

@@ -29,6 +29,12 @@ struct ModelParams {
   int model;
   double r, c0, s, b;
   double a;  // derived range parameter (models.py: r/1, r/3, r/2, r/3^(1/s))
+  double gnorm;  // matern: 2 / Gamma(s)
+  // mode='estimate' (Kriging.py:656-679): semivariances of the kriging MATRIX come from a table
+  // of `lut_size` values over [0, lut_range]; beyond the table: lut_out (the sill)
+  const double* lut;
+  int lut_size;
+  double lut_range, lut_out;
 };
 
 __device__ __forceinline__ int cell_coord(double p, double o, double inv_h) {
@@ -121,8 +127,87 @@ __global__ void grid_sort_cells_kernel(const int* __restrict__ cell_start, int n
 
 // ---------------------------------------------------------------- models ---
 
+// Modified Bessel function of the second kind K_nu(x), real nu >= 0, x > 0 (scipy.special.kv in
+// models.py:419-422).  Temme's series for x < 2, Steed's continued fraction CF2 above, upward
+// recurrence from |mu| <= 1/2 (the classical bessik scheme).
+__device__ double bessel_k(double nu, double x) {
+  const double EPS = 1e-16, PI = 3.141592653589793;
+  const int nl = (int)(nu + 0.5);
+  const double xmu = nu - nl, xmu2 = xmu * xmu;
+  const double xi = 1.0 / x, xi2 = 2.0 * xi;
+  double rkmu, rk1;
+  if (x < 2.0) {
+    const double x2 = 0.5 * x, pimu = PI * xmu;
+    const double fact = fabs(pimu) < 1e-8 ? 1.0 : pimu / sin(pimu);
+    double d = -log(x2);
+    double e = xmu * d;
+    const double fact2 = fabs(e) < 1e-8 ? 1.0 : sinh(e) / e;
+    const double gampl = 1.0 / tgamma(1.0 + xmu), gammi = 1.0 / tgamma(1.0 - xmu);
+    const double gam2 = 0.5 * (gammi + gampl);
+    // (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu); odd part of the 1/Gamma(1+z) series near 0
+    const double gam1 = fabs(xmu) < 0.01
+        ? -(0.5772156649015329 + xmu2 * (-0.0420026350340952 + xmu2 * -0.0421977345555443))
+        : (gammi - gampl) / (2.0 * xmu);
+    double ff = fact * (gam1 * cosh(e) + gam2 * fact2 * d);
+    double sum = ff;
+    e = exp(e);
+    double p = 0.5 * e / gampl, q = 0.5 / (e * gammi), c = 1.0;
+    d = x2 * x2;
+    double sum1 = p;
+    for (int i = 1; i <= 500; ++i) {
+      ff = (i * ff + p + q) / ((double)i * i - xmu2);
+      c *= d / i;
+      p /= (i - xmu);
+      q /= (i + xmu);
+      const double del = c * ff;
+      sum += del;
+      sum1 += c * (p - i * ff);
+      if (fabs(del) < fabs(sum) * EPS) break;
+    }
+    rkmu = sum;
+    rk1 = sum1 * xi2;
+  } else {
+    double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d;
+    double q1 = 0.0, q2 = 1.0;
+    const double a1 = 0.25 - xmu2;
+    double q = a1, c = a1, a = -a1;
+    double sacc = 1.0 + q * delh;
+    for (int i = 2; i <= 500; ++i) {
+      a -= 2 * (i - 1);
+      c = -a * c / i;
+      const double qnew = (q1 - b * q2) / a;
+      q1 = q2;
+      q2 = qnew;
+      q += c * qnew;
+      b += 2.0;
+      d = 1.0 / (b + a * d);
+      delh = (b * d - 1.0) * delh;
+      h += delh;
+      const double dels = q * delh;
+      sacc += dels;
+      if (fabs(dels / sacc) < EPS) break;
+    }
+    h = a1 * h;
+    rkmu = sqrt(PI / (2.0 * x)) * exp(-x) / sacc;
+    rk1 = rkmu * (xmu + x + 0.5 - h) * xi;
+  }
+  for (int i = 1; i <= nl; ++i) {
+    const double t = (xmu + i) * xi2 * rk1 + rkmu;
+    rkmu = rk1;
+    rk1 = t;
+  }
+  return rkmu;
+}
+
 __device__ __forceinline__ double gamma_model(double h, const ModelParams& m) {
   switch (m.model) {
+    case SKG_MODEL_MATERN: {  // models.py:413-422
+      if (h == 0.0) return m.b;
+      const double u = (h * sqrt(m.s)) / m.a;
+      const double kv = bessel_k(m.s, 2.0 * u);
+      if (kv == 0.0) return m.b + m.c0;  // K underflows far outside the range: gamma = sill
+      return m.b + m.c0 * (1.0 - m.gnorm * pow(u, m.s) * kv);
+    }
     case SKG_MODEL_SPHERICAL: {  // models.py:77-82
       if (h <= m.r) {
         const double q = h / m.a;
@@ -150,6 +235,16 @@ __device__ __forceinline__ double gamma_model(double h, const ModelParams& m) {
       return m.b + m.c0 * (1.0 - exp(-pow(h / m.a, m.s)));
     }
   }
+}
+
+// semivariance of a kriging-matrix entry: exact model, or the 'estimate' table
+// (Kriging.py:664-679: index = int((d / range) * precision), no FMA)
+__device__ __forceinline__ double gamma_matrix(double h, const ModelParams& m) {
+  if (m.lut) {
+    const int idx = (int)__dmul_rn(__ddiv_rn(h, m.lut_range), (double)m.lut_size);
+    return idx >= m.lut_size ? m.lut_out : m.lut[idx];
+  }
+  return gamma_model(h, m);
 }
 
 // ------------------------------------------------------------ the kernel ---
@@ -462,7 +557,7 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
           const double dw = ncoord[2 * maxp + i] - ncoord[2 * maxp + j];
           s = __dadd_rn(s, __dmul_rn(dw, dw));
         }
-        gv[q] = gamma_model(sqrt(s), a.model);  // Kriging.py:594, 652-654
+        gv[q] = gamma_matrix(sqrt(s), a.model);  // Kriging.py:594, 652-679
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -681,7 +776,7 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
           const double dw = ncoord[2 * maxp + i] - ncoord[2 * maxp + j];
           s = __dadd_rn(s, __dmul_rn(dw, dw));
         }
-        cv[q] = ct - gamma_model(sqrt(s), a.model);  // Kriging.py:594, 652-654
+        cv[q] = ct - gamma_matrix(sqrt(s), a.model);  // Kriging.py:594, 652-679
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q)
@@ -893,8 +988,8 @@ int64_t skg_krige_scratch_bytes(int max_points) {
 
 int skg_krige(const double* coords, const double* values, int64_t n, int dim, const double* grid,
               const int32_t* cell_start, const int32_t* order, const double* targets, int64_t m,
-              int model, const double* model_params, double radius, int min_points, int max_points,
-              const int32_t* exclude, double* z, double* sigma, int32_t* status, void* scratch,
+              int model, const double* model_params, const double* matrix_lut, int lut_size,
+              double radius, int min_points, int max_points, const int32_t* exclude, double* z, double* sigma, int32_t* status, void* scratch,
               int64_t scratch_bytes, int64_t target_begin, int64_t target_end, void* stream) {
   (void)scratch; (void)scratch_bytes;
   if (!coords || !values || !cell_start || !order || !targets || !model_params || !z || !sigma || !status) {
@@ -911,7 +1006,8 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
     return SKG_E_UNSUPPORTED;
   }
   if (min_points < 0 || min_points > max_points) { set_error("min_points outside [0, max_points]"); return SKG_E_BADARG; }
-  if (model < SKG_MODEL_SPHERICAL || model > SKG_MODEL_STABLE) { set_error("unknown model id %d", model); return SKG_E_BADARG; }
+  if (model < SKG_MODEL_SPHERICAL || model > SKG_MODEL_MATERN) { set_error("unknown model id %d", model); return SKG_E_BADARG; }
+  if ((matrix_lut != nullptr) != (lut_size > 0)) { set_error("matrix_lut and lut_size must come together"); return SKG_E_BADARG; }
   if (!(radius >= 0.0)) { set_error("radius must be >= 0"); return SKG_E_BADARG; }
   KrigeArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -927,8 +1023,16 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
     case SKG_MODEL_EXPONENTIAL: a.model.a = a.model.r / 3.0; break;
     case SKG_MODEL_GAUSSIAN: a.model.a = a.model.r / 2.0; break;
     case SKG_MODEL_CUBIC: a.model.a = a.model.r / 1.0; break;
+    case SKG_MODEL_MATERN:
+      a.model.a = a.model.r / 2.0;
+      a.model.gnorm = 2.0 / std::tgamma(a.model.s);
+      break;
     default: a.model.a = a.model.r / std::pow(3.0, 1.0 / a.model.s); break;
   }
+  a.model.lut = matrix_lut;
+  a.model.lut_size = lut_size;
+  a.model.lut_range = model_params[4];
+  a.model.lut_out = model_params[5];
   a.radius = radius; a.min_points = min_points; a.max_points = max_points;
   a.z = z; a.sigma = sigma; a.status = status; a.t0 = target_begin; a.t1 = target_end;
   a.exclude = exclude;

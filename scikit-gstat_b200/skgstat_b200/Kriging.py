@@ -5,7 +5,7 @@ warp-per-target kriging kernel (csrc/krige_kernels.cu, skg_krige).
 dimension (or a MetricSpace), returns the estimates, fills ``self.sigma`` with the
 kriging variances, counts ``no_points_error`` / ``singular_error`` and emits the
 same KrigingWarning summaries (Kriging.py:461-469).  Defaults follow the reference
-(mode='exact', solver='inv', n_jobs=1); 'estimate' mode, sparse spaces and other
+(mode='exact' and 'estimate', solver='inv', n_jobs=1); sparse spaces and other
 metrics are out of scope and raise NotImplementedError.
 """
 from __future__ import annotations
@@ -62,7 +62,8 @@ class OrdinaryKriging:
             raise NotImplementedError("model %r is not implemented in the kriging kernel "
                                       "(available: %s)" % (self._model_name,
                                                            ", ".join(models.DEVICE_MODELS)))
-        self._shape = variogram.get("shape")
+        self._shape = variogram.get("smoothness") if self._model_name == "matern" \
+            else variogram.get("shape")
         self.dist_metric = variogram.get("dist_func", "euclidean")
         if isinstance(coordinates, MetricSpace):
             assert self.dist_metric == coordinates.dist_metric, \
@@ -80,9 +81,13 @@ class OrdinaryKriging:
         self.gamma_model = Variogram.fitted_model_function(**variogram)
         self.z = None
         self.sigma = None
-        self._mode = None
-        self.mode = mode
+        # calculation mode; self.range has to be initialized (Kriging.py:259-265)
+        self._mode = mode
         self._precision = precision
+        self._prec_dist = None
+        self._prec_g = None
+        self.mode = mode
+        self.precision = precision
         self._solver = None
         self.solver = solver
         self.singular_error = 0
@@ -133,12 +138,16 @@ class OrdinaryKriging:
 
     @mode.setter
     def mode(self, value):
-        if value == "estimate":
-            raise NotImplementedError("mode='estimate' (LUT semivariances) is not built; "
-                                      "the exact mode is what the kernel implements")
-        if value != "exact":
+        """Kriging.py:343-352."""
+        if value == "exact":
+            self._prec_g = None
+            self._prec_dist = None
+        elif value == "estimate":
+            self._precalculate_matrix()
+        else:
             raise ValueError("mode has to be one of 'exact', 'estimate'.")
         self._mode = value
+        self._krige_lut = None
 
     @property
     def precision(self):
@@ -151,6 +160,14 @@ class OrdinaryKriging:
         if value < 1:
             raise ValueError("The precision has be be > 1")
         self._precision = value
+        self._precalculate_matrix()
+        self._krige_lut = None
+
+    def _precalculate_matrix(self):
+        """Kriging.py:656-661: semivariances at `precision` distances in [0, range]; in
+        'estimate' mode the kernel reads the kriging MATRIX entries from this table."""
+        self._prec_dist = np.linspace(0, self.range, self._precision)
+        self._prec_g = np.asarray(self.gamma_model(self._prec_dist), dtype=np.float64)
 
     @property
     def solver(self):
@@ -173,7 +190,12 @@ class OrdinaryKriging:
     def _model_params(self):
         return np.array([self.range, self.sill,
                          self._shape if self._shape is not None else 0.0,
-                         self.nugget if self.nugget != 0 else 0.0], dtype=np.float64)
+                         self.nugget if self.nugget != 0 else 0.0,
+                         self.range, self.sill], dtype=np.float64)  # table range / beyond-table value
+
+    def _matrix_lut(self):
+        """mode='estimate': the precalculated semivariances (host array) or None."""
+        return self._prec_g if self._mode == "estimate" else None
 
     def transform(self, *x):
         """Kriging.py:405-474."""
@@ -193,7 +215,8 @@ class OrdinaryKriging:
             raise NotImplementedError("max_points > %d is not supported by the warp-per-target "
                                       "kernel yet" % _lib.KRIGE_MAX_POINTS)
         z, sigma, status = self._engine().transform(t, self._model_name, self._model_params(),
-                                                    self._minp, self._maxp)
+                                                    self._minp, self._maxp,
+                                                    matrix_lut=self._matrix_lut())
         self.no_points_error = int(np.count_nonzero(status == _lib.KRIGE_LESS_POINTS))
         self.singular_error = int(np.count_nonzero(status == _lib.KRIGE_SINGULAR))
         self.sigma = sigma

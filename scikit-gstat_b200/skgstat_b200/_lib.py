@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libskg_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TILE = 256
 MAX_LAGS = 250
 KRIGE_MAX_POINTS = 64
@@ -22,7 +22,7 @@ STAT_SUM_SQ, STAT_SUM_SQRT, STAT_COUNT_BELOW = 1, 2, 4
 KEY_SQDIST, KEY_ABSDZ = 0, 1
 VALUE_SCALAR, VALUE_CROSS, VALUE_AGGREGATE = 0, 1, 2
 MAX_VALUE_COLUMNS = 8
-MODEL_IDS = dict(spherical=0, exponential=1, gaussian=2, cubic=3, stable=4)
+MODEL_IDS = dict(spherical=0, exponential=1, gaussian=2, cubic=3, stable=4, matern=5)
 KRIGE_OK, KRIGE_LESS_POINTS, KRIGE_SINGULAR = 0, 1, 2
 
 _p = C.c_void_p
@@ -54,7 +54,7 @@ SIGNATURES = {
                                     _i64, _i64, _p]),
     "skg_krige_build_grid": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p]),
     "skg_krige_scratch_bytes": (_i64, [_int]),
-    "skg_krige": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _i64, _int, _p, _dbl, _int, _int,
+    "skg_krige": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _i64, _int, _p, _p, _int, _dbl, _int, _int,
                          _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
 }
 

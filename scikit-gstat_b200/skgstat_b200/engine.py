@@ -960,7 +960,7 @@ class KrigeEngine:
         return g
 
     def transform(self, targets, model: str, model_params, min_points: int, max_points: int,
-                  exclude=None):
+                  exclude=None, matrix_lut=None):
         """targets (M, dim) -> (z, sigma, status) numpy arrays for ALL M targets; with a
         process group each rank krigs its contiguous slice and the slices are gathered."""
         t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64))
@@ -968,14 +968,19 @@ class KrigeEngine:
             raise ValueError("targets must be (M, %d)" % self.dim)
         m = int(t.shape[0])
         mp = np.asarray(model_params, dtype=np.float64)
-        if mp.size != 4:
-            raise ValueError("model_params = [range, sill, shape, nugget]")
+        if mp.size == 4:
+            mp = np.concatenate((mp, [mp[0], mp[1]]))
+        if mp.size != 6:
+            raise ValueError("model_params = [range, sill, shape, nugget(, table range, table sill)]")
         with torch.cuda.device(self.device):
             tg = to_device(t.T, self.device)
             ex = None
             if exclude is not None:
                 ex = to_device(np.ascontiguousarray(exclude, dtype=np.int32), self.device)
-            z, sigma, status = self.transform_device(tg, m, model, mp, min_points, max_points, ex)
+            lut = None
+            if matrix_lut is not None:
+                lut = to_device(np.ascontiguousarray(matrix_lut, dtype=np.float64), self.device)
+            z, sigma, status = self.transform_device(tg, m, model, mp, min_points, max_points, ex, lut)
             if self.world > 1:
                 b, e = D.shard_range(m, self.rank, self.world)
                 z = D.allgather_varlen(z[b:e], self.group)
@@ -984,7 +989,8 @@ class KrigeEngine:
         return to_host(z), to_host(sigma), to_host(status)
 
     def transform_device(self, targets_soa: torch.Tensor, m: int, model: str, mp: np.ndarray,
-                         min_points: int, max_points: int, exclude: Optional[torch.Tensor] = None):
+                         min_points: int, max_points: int, exclude: Optional[torch.Tensor] = None,
+                         matrix_lut: Optional[torch.Tensor] = None):
         """Device-resident variant: targets_soa is a (dim*M) fp64 CUDA tensor; returns
         device tensors (only this rank's slice [begin, end) is filled)."""
         z = torch.full((m,), float("nan"), dtype=torch.float64, device=self.device)
@@ -992,10 +998,13 @@ class KrigeEngine:
         status = torch.zeros(m, dtype=torch.int32, device=self.device)
         b, e = D.shard_range(m, self.rank, self.world)
         mp = np.ascontiguousarray(mp, dtype=np.float64)
+        if mp.size == 4:
+            mp = np.concatenate((mp, [mp[0], mp[1]]))
         rc = self.lib.skg_krige(
             _ptr(self.coords), _ptr(self.values), self.n, self.dim, _hptr(self.grid),
             _ptr(self.cell_start), _ptr(self.order), _ptr(targets_soa), m,
-            _lib.MODEL_IDS[model], _hptr(mp), self.radius, int(min_points), int(max_points),
+            _lib.MODEL_IDS[model], _hptr(mp), _ptr(matrix_lut),
+            0 if matrix_lut is None else int(matrix_lut.numel()), self.radius, int(min_points), int(max_points),
             _ptr(exclude), _ptr(z), _ptr(sigma), _ptr(status), _ptr(self._scratch), self._scratch.numel(),
             b, e, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         _lib.check(rc, "skg_krige")

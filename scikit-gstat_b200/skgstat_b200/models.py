@@ -72,4 +72,4 @@ def matern(h, r, c0, s, b=0.0):
 MODELS = dict(spherical=spherical, exponential=exponential, gaussian=gaussian, cubic=cubic,
               stable=stable, matern=matern)
 # models the kriging kernel implements on the device
-DEVICE_MODELS = ("spherical", "exponential", "gaussian", "cubic", "stable")
+DEVICE_MODELS = ("spherical", "exponential", "gaussian", "cubic", "stable", "matern")

@@ -63,3 +63,8 @@ def golden_cv():
 @pytest.fixture(scope="session")
 def golden_mv():
     return Golden("multivariate")
+
+
+@pytest.fixture(scope="session")
+def golden_kriging_ext():
+    return Golden("kriging_ext")

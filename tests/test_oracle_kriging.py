@@ -45,3 +45,22 @@ def test_jacknife_oracle_matches_reference_golden(golden_cv):
         dev = ok.jacknife_deviations(c, v, idx, case["model"], case["effective_range"],
                                      case["sill"], case["nugget"])
         assert_allclose(dev, g.out(case, "deviations")[:60], rtol=1e-8, atol=1e-9, err_msg=str(case))
+
+
+def test_oracle_matern_and_estimate_mode_match_reference(golden_kriging_ext):
+    """Matern model and mode='estimate' restatements pinned to reference outputs
+    (oracle/make_golden.py::make_kriging_ext)."""
+    g = golden_kriging_ext
+    c, v = g.inputs("rnd1000")
+    t = g._z["targets"]
+    for case in g.manifest:
+        z, s, st = ok.krige(c, v, t, case["model"], case["effective_range"], case["sill"], case["nugget"],
+                            case["shape"], 4, case["max_points"], mode=case["mode"],
+                            precision=case.get("precision", 100))
+        assert (st == 0).all()
+        assert_allclose(z, g.out(case, "z"), rtol=1e-9)
+        assert_allclose(s, g.out(case, "sigma"), rtol=1e-9, atol=1e-9 * case["sill"])
+    # the Matern semivariance itself (reference models.matern on a grid of h and smoothness)
+    hs = g._z["matern/h"]
+    for k, sm in enumerate(g._z["matern/s"]):
+        assert_allclose(ok.matern(hs, 200.0, 3.0, sm, 0.1), g._z["matern/%d" % k], rtol=1e-12)
