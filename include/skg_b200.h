@@ -73,6 +73,12 @@ extern "C" {
 #define SKG_VALUE_CROSS 1     /* n_values = 2: |dz_0| * |dz_1|         (:1979-1984 cross-variogram) */
 #define SKG_VALUE_AGGREGATE 2 /* n_values <= 8: sqrt(sum_k dz_k^2)     (:1974-1977 'aggregate')   */
 #define SKG_MAX_VALUE_COLUMNS 8
+/* skg_pair_hist only, n_values = 0, values ignored: the "difference" is a power of the pair's
+ * distance, so sum_sq / sum_sqrt become moments of the distance distribution per lag class
+ * (np.std / skewness inside np.histogram_bin_edges, binning.py:114-122) */
+#define SKG_VALUE_DIST_S 3    /* s = d^2:  sum_sq = sum d^4, sum_sqrt = sum d   */
+#define SKG_VALUE_DIST_D 4    /* d:        sum_sq = sum d^2                     */
+#define SKG_VALUE_DIST_D15 5  /* d^1.5:    sum_sq = sum d^3                     */
 
 /* key kinds for the select passes */
 #define SKG_KEY_SQDIST 0 /* s = squared distance (order statistics of d)       */

@@ -381,6 +381,45 @@ def make_kriging_ext(skg, ds):
     np.savez_compressed(os.path.join(OUT, "kriging_ext.npz"), **arrays)
 
 
+def make_binners(skg, ds):
+    """histogram-rule binners (binning.auto_derived_lags, binning.py:82-122)."""
+    arrays, manifest = {}, []
+    methods = ("sqrt", "sturges", "rice", "scott", "doane", "fd", "auto")
+    for dname in ("pancake300", "rnd400", "lattice225", "rnd3d150", "rnd1d120", "gamma30"):
+        c, v = ds[dname]
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = v
+        for method in methods:
+            for ml in (None, "median", 0.6):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    V = skg.Variogram(c, v, bin_func=method, maxlag=ml, n_lags=10)
+                if len(V.bins) > 240:
+                    continue
+                key = "b/%d" % len(manifest)
+                arrays[key + "/bins"] = V.bins
+                arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+                arrays[key + "/experimental"] = V.experimental
+                manifest.append(dict(key=key, kind="variogram", dataset=dname, bin_func=method,
+                                     maxlag=ml, n_lags=int(V.n_lags)))
+    c, v = ds["rnd400"]
+    for method in ("sturges", "scott", "doane", "fd"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            V = skg.DirectionalVariogram(c, v, bin_func=method, maxlag="median", azimuth=30,
+                                         tolerance=40.0, bandwidth=20.0)
+        key = "b/%d" % len(manifest)
+        arrays[key + "/bins"] = V.bins
+        arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+        arrays[key + "/experimental"] = V.experimental
+        manifest.append(dict(key=key, kind="directional", dataset="rnd400", bin_func=method,
+                             maxlag="median", n_lags=int(V.n_lags), azimuth=30, tolerance=40.0,
+                             bandwidth=20.0))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "binners.npz"), **arrays)
+    print("binner cases:", len(manifest))
+
+
 def make_api_fixture(skg):
     """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
     test_variogram.py::test_fit_lm; data only."""
@@ -394,7 +433,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -409,6 +448,8 @@ def main():
         make_multivariate(skg, ds)
     if "kriging_ext" in which:
         make_kriging_ext(skg, ds)
+    if "binners" in which:
+        make_binners(skg, ds)
 
 
 if __name__ == "__main__":

@@ -465,6 +465,7 @@ static int check_values(int n_values, int value_mode, MvSpec* mv) {
   if (value_mode == SKG_VALUE_SCALAR && n_values == 1) return 0;
   if (value_mode == SKG_VALUE_CROSS && n_values == 2) return 0;
   if (value_mode == SKG_VALUE_AGGREGATE && n_values >= 1 && n_values <= SKG_MAX_VALUE_COLUMNS) return 0;
+  if (value_mode >= SKG_VALUE_DIST_S && value_mode <= SKG_VALUE_DIST_D15 && n_values == 0) return 0;
   set_error("n_values=%d / value_mode=%d: scalar needs 1 column, cross 2, aggregate 1..%d", n_values,
             value_mode, SKG_MAX_VALUE_COLUMNS);
   return SKG_E_BADARG;
@@ -704,7 +705,8 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
                   void* stream) {
   int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
-  if (!values || !thr_bits || !count || n_lags < 1) { set_error("values/thr_bits/count NULL or n_lags < 1"); return SKG_E_BADARG; }
+  const bool dist_mode = value_mode >= SKG_VALUE_DIST_S && value_mode <= SKG_VALUE_DIST_D15;
+  if ((!values && !dist_mode) || !thr_bits || !count || n_lags < 1) { set_error("values/thr_bits/count NULL or n_lags < 1"); return SKG_E_BADARG; }
   if (stats == SKG_STAT_COUNT_BELOW) {
     if (!dz_lo || !sum_sq) { set_error("below-count mode needs dz_lo and sum_sq (receives the counts)"); return SKG_E_BADARG; }
   } else if ((stats & ~3) || ((stats & SKG_STAT_SUM_SQ) && !sum_sq) || ((stats & SKG_STAT_SUM_SQRT) && !sum_sqrt)) {

@@ -396,7 +396,16 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
             if (gg < nbS && !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nbS;
           }
           g[r] = gg;
-          dz[r] = VM ? mv_diff(mvI, mvJ, r * HB + tid, jj, mv) : zi[r] - zj;
+          if (VM) {
+            // SKG_VALUE_DIST_*: the "difference" is a power of the distance itself, so the
+            // estimator sums become moments of the distance distribution (histogram-rule binners)
+            if (mv.mode == SKG_VALUE_DIST_S) dz[r] = s;
+            else if (mv.mode == SKG_VALUE_DIST_D) dz[r] = sqrt(s);
+            else if (mv.mode == SKG_VALUE_DIST_D15) { const double d = sqrt(s); dz[r] = d * sqrt(d); }
+            else dz[r] = mv_diff(mvI, mvJ, r * HB + tid, jj, mv);
+          } else {
+            dz[r] = zi[r] - zj;
+          }
           if (STATS == 4) dz[r] = (fabs(dz[r]) < sDzLo[min(gg, nbS - GS) / GS]) ? 1.0 : 0.0;
         }
       };
@@ -658,7 +667,7 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
 constexpr int MAX_GRID_PER_SM = 16;
 
 inline size_t mv_smem_bytes(const MvSpec& mv) {
-  return mv.nv > 1 ? (size_t)mv.nv * (2 * TILE + 2) * sizeof(double) : 0;
+  return mv.nv >= 1 ? (size_t)mv.nv * (2 * TILE + 2) * sizeof(double) : 0;
 }
 
 struct HistLaunch {

@@ -318,9 +318,16 @@ class Variogram:
         """Variogram.py:771-817."""
         if isinstance(bin_func, str):
             name = bin_func.lower()
+            if name in binning.AUTO_BINNERS:
+                # np.histogram_bin_edges rules (binning.py:82-122): the rule's inputs (count, min,
+                # max, quartiles, moments of the distances) come from the pair kernels
+                self._bin_func = name
+                self._bin_func_name = bin_func
+                self._bins = None
+                self._reset_pair_state()
+                return
             if name not in _GPU_BINNERS:
-                if name in ("sturges", "scott", "fd", "sqrt", "doane", "kmeans", "ward",
-                            "stable_entropy"):
+                if name in ("stone", "kmeans", "ward", "stable_entropy"):
                     raise NotImplementedError(
                         "bin_func=%r needs every distance in host memory and is out of "
                         "scope of the GPU path (even / uniform / callable / edges)" % bin_func)
@@ -372,11 +379,58 @@ class Variogram:
                 raise ValueError("no point pair inside maxlag / the directional mask")
             return np.fromiter((binning.percentile_from_order_stats(total, q, lambda r: d[r])
                                 for q in qs), dtype=float), None
+        if self._bin_func in binning.AUTO_BINNERS:
+            return self._auto_bins(self._bin_func, maxlag, masked)
         # user callable: the reference's operator contract hands it the materialised vector
         d = self.distance.copy()
         if masked:
             d[np.where(~self._direction_mask())] = np.nan
         return self._bin_func(d, n, maxlag)
+
+    def _auto_bins(self, method, maxlag, masked):
+        """binning.auto_derived_lags (binning.py:82-122) without the distance vector: exact
+        count / min / max / quartiles from the select passes, std and skewness from three
+        moment sweeps; the edges are np.linspace(min, max, n_bins + 1)[1:] as in numpy."""
+        dmax = self._distance_max(masked)
+        if dmax is None:
+            raise ValueError("no point pair passes the directional mask")
+        if maxlag is None or maxlag > dmax:
+            maxlag = dmax
+        need_q = method in ("fd", "auto")
+
+        def rank_fn(total):
+            if total == 0:
+                return []
+            out = {0, total - 1}
+            if need_q:
+                for q in (25, 75):
+                    out.update(binning.percentile_ranks(total, q)[:2])
+            return sorted(out)
+
+        d, total = self._distance_order_stats(rank_fn, masked=masked, limit=maxlag)
+        if total == 0:
+            raise ValueError("no point pair inside maxlag / the directional mask")
+        stats = {}
+        if need_q:
+            stats["q25"] = binning.percentile_from_order_stats(total, 25, lambda r: d[r])
+            stats["q75"] = binning.percentile_from_order_stats(total, 75, lambda r: d[r])
+        if method in ("scott", "doane"):
+            eng = self._X.engine(self._process_group)
+            n, s1, s2, s3 = eng.dist_moments(maxlag, self._dirp() if masked else None,
+                                             third=(method == "doane"))
+            if n != total:
+                raise RuntimeError("moment sweep and select pass disagree on the pair count")
+            mean = s1 / n
+            var = max(s2 / n - mean * mean, 0.0)
+            stats["std"] = float(np.sqrt(var))
+            if method == "doane":
+                m3 = s3 / n - 3.0 * mean * (s2 / n) + 2.0 * mean ** 3
+                stats["g1"] = m3 / stats["std"] ** 3 if stats["std"] > 0 else 0.0
+        edges = binning.auto_edges(method, total, d[0], d[total - 1], **stats)
+        if len(edges) > _lib.MAX_LAGS:
+            raise ValueError("bin_func=%r derives %d lag classes; the GPU lag table holds %d"
+                             % (method, len(edges), _lib.MAX_LAGS))
+        return edges, len(edges)
 
     @property
     def bins(self):

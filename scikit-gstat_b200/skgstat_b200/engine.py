@@ -373,6 +373,41 @@ class PairEngine:
         host = to_host(out)
         return host[:nl].astype(np.int64), host[nl:2 * nl].copy(), host[2 * nl:].copy()
 
+    def dist_moments(self, limit: float, dirp=None, third: bool = True):
+        """(n, sum d, sum d^2, sum d^3) over the (mask-passing) pairs with d <= limit: the
+        inputs of np.std / the skewness inside np.histogram_bin_edges (binning.py:114-122).
+        Fused-pass sweeps whose "value difference" is a power of the distance (SKG_VALUE_DIST_*)."""
+        from ._exact import sq_upper_inclusive_bits
+        thr = np.array([sq_upper_inclusive_bits(limit)], dtype=np.uint64)  # class 0: d <= limit
+        amb = self.ambiguous_pairs(dirp)
+
+        def sweep(mode, stats):
+            out = self._buffer("hist_out", 3, torch.float64).zero_()
+            cnt = self._buffer("hist_cnt", 1, torch.int64).zero_()
+            scratch = self._hist_scratch(1)
+            with torch.cuda.device(self.device):
+                rc = self.lib.skg_pair_hist(
+                    _ptr(self.coords), None, 0, mode, self.n, self.dim, _hptr(dirp), _hptr(thr), 1,
+                    int(stats), None, _ptr(cnt), _ptr(out[1:2]), _ptr(out[2:3]), _ptr(scratch),
+                    scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
+            _lib.check(rc, "skg_pair_hist")
+            self.launches += 5 if self.t1 > self.t0 else 0
+            out[:1] = cnt.to(torch.float64)
+            if amb is not None and amb[0].size:
+                s_bits, _ = self._amb_keys(amb)
+                sv = s_bits[s_bits < thr[0]].view(np.float64)
+                d = np.sqrt(sv)
+                val = {_lib.VALUE_DIST_S: sv, _lib.VALUE_DIST_D: d, _lib.VALUE_DIST_D15: d * np.sqrt(d)}[mode]
+                extra = np.array([sv.size, float(np.sum(val * val)), float(np.sum(np.sqrt(val)))])
+                out += to_device(extra, self.device)
+            D.allreduce_sum_(out, self.group)
+            return to_host(out)
+
+        a = sweep(_lib.VALUE_DIST_S, _lib.STAT_SUM_SQ | _lib.STAT_SUM_SQRT)   # sum d^4, sum d
+        b = sweep(_lib.VALUE_DIST_D, _lib.STAT_SUM_SQ)                        # sum d^2
+        s3 = float(sweep(_lib.VALUE_DIST_D15, _lib.STAT_SUM_SQ)[1]) if third else None
+        return int(a[0]), float(a[2]), float(b[1]), s3
+
     # -------------------------------------------------------- K2b (batched)
     BATCH_CHUNK = 64  # value vectors uploaded per call
 

@@ -68,3 +68,8 @@ def golden_mv():
 @pytest.fixture(scope="session")
 def golden_kriging_ext():
     return Golden("kriging_ext")
+
+
+@pytest.fixture(scope="session")
+def golden_binners():
+    return Golden("binners")
