@@ -79,6 +79,9 @@ extern "C" {
 #define SKG_VALUE_DIST_S 3    /* s = d^2:  sum_sq = sum d^4, sum_sqrt = sum d   */
 #define SKG_VALUE_DIST_D 4    /* d:        sum_sq = sum d^2                     */
 #define SKG_VALUE_DIST_D15 5  /* d^1.5:    sum_sq = sum d^3                     */
+/* skg_pair_hist only, OR-ed onto SCALAR / CROSS / AGGREGATE: the difference is squared first, so
+ * sum_sqrt = sum |difference| (np.nanmean in estimators.minmax, estimators.py:257-296) */
+#define SKG_VALUE_SQUARE_FLAG 0x100
 
 /* key kinds for the select passes */
 #define SKG_KEY_SQDIST 0 /* s = squared distance (order statistics of d)       */

@@ -420,6 +420,51 @@ def make_binners(skg, ds):
     print("binner cases:", len(manifest))
 
 
+def make_estimators(skg, ds):
+    """minmax / percentile / entropy estimators (estimators.py:257-367,
+    Variogram.py:2044-2092)."""
+    arrays, manifest = {}, []
+    est_cfgs = [("minmax", {}), ("percentile", {}), ("percentile", dict(percentile=25)),
+                ("percentile", dict(percentile=90.5)), ("entropy", {}), ("entropy", dict(entropy_bins=20)),
+                ("entropy", dict(entropy_bins="sturges"))]
+    for dname in ("pancake300", "rnd400", "rnd3d150", "gamma30"):
+        c, v = ds[dname]
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = v
+        for est, kw in est_cfgs:
+            for bf, n_lags, ml in (("even", 10, None), ("uniform", 8, "median"), ("even", 15, "median")):
+                try:
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        V = skg.Variogram(c, v, estimator=est, bin_func=bf, n_lags=n_lags, maxlag=ml, **kw)
+                        exp = V.experimental
+                except Exception as e:      # e.g. minmax on an empty lag class raises in the reference
+                    print("skip", dname, est, bf, ml, type(e).__name__)
+                    continue
+                key = "s/%d" % len(manifest)
+                arrays[key + "/bins"] = V.bins
+                arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+                arrays[key + "/experimental"] = exp
+                manifest.append(dict(key=key, kind="variogram", dataset=dname, estimator=est,
+                                     bin_func=bf, n_lags=n_lags, maxlag=ml, kwargs=kw))
+    c, v = ds["rnd400"]
+    for est, kw in est_cfgs[:5]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            V = skg.DirectionalVariogram(c, v, estimator=est, n_lags=8, maxlag="median", azimuth=60,
+                                         tolerance=45.0, bandwidth=25.0, **kw)
+            exp = V.experimental
+        key = "s/%d" % len(manifest)
+        arrays[key + "/bins"] = V.bins
+        arrays[key + "/bin_count"] = np.asarray(V.bin_count, dtype=np.int64)
+        arrays[key + "/experimental"] = exp
+        manifest.append(dict(key=key, kind="directional", dataset="rnd400", estimator=est, n_lags=8,
+                             maxlag="median", azimuth=60, tolerance=45.0, bandwidth=25.0, kwargs=kw))
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "estimators.npz"), **arrays)
+    print("estimator cases:", len(manifest))
+
+
 def make_api_fixture(skg):
     """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
     test_variogram.py::test_fit_lm; data only."""
@@ -433,7 +478,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners", "estimators"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -450,6 +495,8 @@ def main():
         make_kriging_ext(skg, ds)
     if "binners" in which:
         make_binners(skg, ds)
+    if "estimators" in which:
+        make_estimators(skg, ds)
 
 
 if __name__ == "__main__":

@@ -461,6 +461,8 @@ int check_pair_args(const double* coords, int64_t n, int dim, int64_t t0, int64_
 // value columns: [n_values][n]; mode SKG_VALUE_*
 static int check_values(int n_values, int value_mode, MvSpec* mv) {
   mv->nv = n_values;
+  mv->square = (value_mode & SKG_VALUE_SQUARE_FLAG) ? 1 : 0;
+  value_mode &= ~SKG_VALUE_SQUARE_FLAG;
   mv->mode = value_mode;
   if (value_mode == SKG_VALUE_SCALAR && n_values == 1) return 0;
   if (value_mode == SKG_VALUE_CROSS && n_values == 2) return 0;
@@ -705,7 +707,8 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
                   void* stream) {
   int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
-  const bool dist_mode = value_mode >= SKG_VALUE_DIST_S && value_mode <= SKG_VALUE_DIST_D15;
+  const bool dist_mode = (value_mode & ~SKG_VALUE_SQUARE_FLAG) >= SKG_VALUE_DIST_S &&
+                         (value_mode & ~SKG_VALUE_SQUARE_FLAG) <= SKG_VALUE_DIST_D15;
   if ((!values && !dist_mode) || !thr_bits || !count || n_lags < 1) { set_error("values/thr_bits/count NULL or n_lags < 1"); return SKG_E_BADARG; }
   if (stats == SKG_STAT_COUNT_BELOW) {
     if (!dz_lo || !sum_sq) { set_error("below-count mode needs dz_lo and sum_sq (receives the counts)"); return SKG_E_BADARG; }
@@ -716,7 +719,7 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
   MvSpec mv;
   rc = check_values(n_values, value_mode, &mv);
   if (rc) return rc;
-  const bool use_mv = value_mode != SKG_VALUE_SCALAR && stats != 0;
+  const bool use_mv = (value_mode != SKG_VALUE_SCALAR) && stats != 0;  // any flag or multi-column mode
   const int max_blocks = sm_count() * MAX_GRID_PER_SM;
   SweepScratch S;
   rc = carve_scratch(scratch, scratch_bytes, n, (int64_t)max_blocks * n_lags * (int64_t)sizeof(HistPartial), &S);

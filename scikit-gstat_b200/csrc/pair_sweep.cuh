@@ -200,11 +200,13 @@ __device__ __forceinline__ void rmw_split(unsigned saddr, unsigned caddr, double
 // Both tiles' value columns live in shared memory (mvI[k][TILE], mvJ[k][TILE + 2]).
 struct MvSpec {
   int nv;
-  int mode;
+  int mode;    // SKG_VALUE_* without flags
+  int square;  // SKG_VALUE_SQUARE_FLAG: the difference is squared before the statistics
 };
 
 __device__ __forceinline__ double mv_diff(const double* __restrict__ mvI, const double* __restrict__ mvJ,
                                           int i, int jj, const MvSpec mv) {
+  if (mv.mode == SKG_VALUE_SCALAR) return fabs(mvI[i] - mvJ[jj]);  // only reached with the SQUARE flag
   if (mv.mode == SKG_VALUE_CROSS) {
     const double a = fabs(mvI[i] - mvJ[jj]);
     const double b = fabs(mvI[TILE + i] - mvJ[(TILE + 2) + jj]);
@@ -403,6 +405,7 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
             else if (mv.mode == SKG_VALUE_DIST_D) dz[r] = sqrt(s);
             else if (mv.mode == SKG_VALUE_DIST_D15) { const double d = sqrt(s); dz[r] = d * sqrt(d); }
             else dz[r] = mv_diff(mvI, mvJ, r * HB + tid, jj, mv);
+            if (mv.square) dz[r] = __dmul_rn(dz[r], dz[r]);  // sum_sqrt then is the sum of |difference|
           } else {
             dz[r] = zi[r] - zj;
           }

@@ -38,7 +38,7 @@ from . import _lib, binning, estimators, models
 from ._exact import sq_threshold_bits
 from .MetricSpace import MetricSpace
 
-_GPU_ESTIMATORS = ("matheron", "cressie", "dowd")
+_GPU_ESTIMATORS = ("matheron", "cressie", "dowd", "minmax", "percentile", "entropy")
 _GPU_BINNERS = ("even", "uniform")
 
 
@@ -387,7 +387,7 @@ class Variogram:
             d[np.where(~self._direction_mask())] = np.nan
         return self._bin_func(d, n, maxlag)
 
-    def _auto_bins(self, method, maxlag, masked):
+    def _auto_bins(self, method, maxlag, masked, limit_check=True):
         """binning.auto_derived_lags (binning.py:82-122) without the distance vector: exact
         count / min / max / quartiles from the select passes, std and skewness from three
         moment sweeps; the edges are np.linspace(min, max, n_bins + 1)[1:] as in numpy."""
@@ -427,7 +427,7 @@ class Variogram:
                 m3 = s3 / n - 3.0 * mean * (s2 / n) + 2.0 * mean ** 3
                 stats["g1"] = m3 / stats["std"] ** 3 if stats["std"] > 0 else 0.0
         edges = binning.auto_edges(method, total, d[0], d[total - 1], **stats)
-        if len(edges) > _lib.MAX_LAGS:
+        if limit_check and len(edges) > _lib.MAX_LAGS:
             raise ValueError("bin_func=%r derives %d lag classes; the GPU lag table holds %d"
                              % (method, len(edges), _lib.MAX_LAGS))
         return edges, len(edges)
@@ -464,10 +464,11 @@ class Variogram:
             if name in _GPU_ESTIMATORS:
                 self._estimator = estimators.ESTIMATORS[name]
                 self._estimator_name = name
-            elif name in ("genton", "minmax", "percentile", "entropy"):
+            elif name == "genton":
                 raise NotImplementedError(
-                    "estimator %r is outside the accelerated path (matheron, cressie, dowd); "
-                    "pass a callable to run it on materialised lag classes" % estimator_name)
+                    "estimator 'genton' needs all pairs of pair differences per lag class and is "
+                    "outside the accelerated path; pass estimators.genton-like callables to run "
+                    "them on materialised lag classes")
             else:
                 raise ValueError("Variogram estimator %s is not understood, please provide "
                                  "the function." % estimator_name)
@@ -496,6 +497,25 @@ class Variogram:
         elif name == "dowd":
             cnt, med = eng.dz_medians(edges, dirp, thr_bits=thr)
             exp = estimators.finalize_dowd(cnt, med)
+        elif name == "minmax":  # estimators.py:296: (nanmax - nanmin) / nanmean per lag class
+            cnt, total = eng.dz_abs_sums(edges, dirp, thr_bits=thr)
+            vals, tot = eng.dz_order_stats(edges, lambda g, t: [0, t - 1] if t else [], dirp, thr_bits=thr)
+            lo = [vals[g][0] if tot[g] else np.nan for g in range(len(edges))]
+            hi = [vals[g][tot[g] - 1] if tot[g] else np.nan for g in range(len(edges))]
+            exp = estimators.finalize_minmax(cnt, lo, hi, total)
+        elif name == "percentile":  # Variogram.py:2076-2082: kwargs['percentile'] or 50
+            p = self._kwargs.get("percentile") if self._kwargs.get("percentile", False) else 50
+            vals, tot = eng.dz_order_stats(
+                edges, lambda g, t: sorted(set(binning.percentile_ranks(t, p)[:2])) if t else [],
+                dirp, thr_bits=thr)
+            cnt = np.asarray(tot, dtype=np.int64)
+            exp = np.array([binning.percentile_from_order_stats(tot[g], p, lambda r, g=g: vals[g][r])
+                            if tot[g] else np.nan for g in range(len(edges))])
+        elif name == "entropy":  # Variogram.py:2065-2075 + util/shannon.py:27-34
+            value_edges = self._entropy_value_edges()
+            hist = eng.dz_value_histogram(edges, value_edges, dirp, thr_bits=thr)
+            cnt = eng.hist_counts(thr, dirp)
+            exp = np.array([estimators.shannon_from_counts(hist[g]) for g in range(len(edges))])
         else:  # user callable on materialised lag classes (reference operator contract)
             classes = list(self.lag_classes())
             cnt = np.fromiter((c.size for c in classes), dtype=np.int64)
@@ -540,6 +560,28 @@ class Variogram:
             (self._values, self._co_variable, self._is_cross, self._is_aggregate, self._exp,
              self._bin_count, self.cof, self.cov, self._values_token, self._diff, self._groups) = keep
         return out
+
+    def _entropy_value_edges(self):
+        """Variogram.py:2066-2073: np.histogram_bin_edges(self.distance, bins=entropy_bins - 1) -
+        the reference derives the |dz| histogram edges from the DISTANCE vector; built here from
+        the exact min / max (and, for rule names, quartiles / moments) of the distances."""
+        nb = self._kwargs.get("entropy_bins", 50)
+        d, total = self._distance_order_stats(lambda t: [0, t - 1] if t else [])
+        if total == 0:
+            raise ValueError("no point pairs")
+        dmin, dmax = d[0], d[total - 1]
+        if isinstance(nb, (int, np.integer)) and not isinstance(nb, bool):
+            nb = int(nb) - 1
+            if nb < 1:
+                raise ValueError("`bins` must be positive, when an integer")
+            first, last = np.float64(dmin), np.float64(dmax)
+            if first == last:
+                first, last = first - 0.5, last + 0.5
+            return np.linspace(first, last, nb + 1, endpoint=True, dtype=np.float64)
+        if isinstance(nb, str):
+            edges, _ = self._auto_bins(nb.lower(), None, False, limit_check=False)
+            return np.concatenate(([np.float64(dmin) if dmin != dmax else dmin - 0.5], edges))
+        return np.asarray(nb, dtype=float)
 
     @property
     def bin_count(self):

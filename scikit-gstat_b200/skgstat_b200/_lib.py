@@ -22,6 +22,7 @@ STAT_SUM_SQ, STAT_SUM_SQRT, STAT_COUNT_BELOW = 1, 2, 4
 KEY_SQDIST, KEY_ABSDZ = 0, 1
 VALUE_SCALAR, VALUE_CROSS, VALUE_AGGREGATE = 0, 1, 2
 VALUE_DIST_S, VALUE_DIST_D, VALUE_DIST_D15 = 3, 4, 5
+VALUE_SQUARE_FLAG = 0x100
 MAX_VALUE_COLUMNS = 8
 MODEL_IDS = dict(spherical=0, exponential=1, gaussian=2, cubic=3, stable=4, matern=5)
 KRIGE_OK, KRIGE_LESS_POINTS, KRIGE_SINGULAR = 0, 1, 2

@@ -788,6 +788,64 @@ class PairEngine:
         host = to_host(both)
         return host[:nl].astype(np.int64), host[nl:].astype(np.int64)
 
+    def dz_abs_sums(self, edges, dirp=None, thr_bits=None):
+        """Per lag class (count, sum of the pair differences): fused pass over the SQUARED
+        difference with the sum-of-square-roots statistic (sqrt(fl(x*x)) == |x|)."""
+        if self.values is None:
+            raise ValueError("values not set")
+        thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        nl = int(thr.size)
+        out = self._buffer("hist_out", 3 * nl, torch.float64).zero_()
+        cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
+        scratch = self._hist_scratch(nl)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_hist(
+                _ptr(self.coords), _ptr(self.values), self.nv, self.vmode | _lib.VALUE_SQUARE_FLAG,
+                self.n, self.dim, _hptr(dirp), _hptr(thr), nl, _lib.STAT_SUM_SQRT, None, _ptr(cnt),
+                None, _ptr(out[2 * nl:]), _ptr(scratch), scratch.numel(), self.t0, self.t1,
+                self.tstride, self._stream())
+        _lib.check(rc, "skg_pair_hist")
+        self.launches += 5 if self.t1 > self.t0 else 0
+        out[:nl] = cnt.to(torch.float64)
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, dz = self._amb_keys(amb)
+            g = np.searchsorted(thr, s_bits, side="right")
+            keep = g < nl
+            extra = np.zeros(3 * nl)
+            np.add.at(extra, g[keep], 1.0)
+            np.add.at(extra, 2 * nl + g[keep], dz[keep])
+            out += to_device(extra, self.device)
+        D.allreduce_sum_(out, self.group)
+        host = to_host(out)
+        return host[:nl].astype(np.int64), host[2 * nl:].copy()
+
+    def dz_order_stats(self, edges, rank_fn, dirp=None, thr_bits=None):
+        """Exact order statistics of the pair differences per lag class: rank_fn(lag, total) ->
+        0-based ranks.  Returns (list of dict rank -> value, totals)."""
+        if self.values is None:
+            raise ValueError("values not set")
+        thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        nl = int(thr.size)
+        hi = to_bits(self._dz_bound) + 1
+        return self._dz_select(thr, dirp, [0] * nl, [hi] * nl, rank_fn)
+
+    def dz_value_histogram(self, edges, value_edges, dirp=None, thr_bits=None):
+        """np.histogram(|dz| of lag class g, bins=value_edges)[0] for every lag class g: exact
+        counts [n_lags, len(value_edges) - 1] from one below-count sweep per value edge (numpy's
+        bins are half open, the last one closed)."""
+        thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        nl = int(thr.size)
+        ve = np.asarray(value_edges, dtype=np.float64)
+        if ve.ndim != 1 or ve.size < 2 or np.any(ve[:-1] > ve[1:]):
+            raise ValueError("value_edges must be an increasing 1-D array")
+        cuts = ve.copy()
+        cuts[-1] = np.nextafter(ve[-1], np.inf)      # x <= last edge  <=>  x < nextafter(last edge)
+        below = np.empty((cuts.size, nl), dtype=np.int64)
+        for k, cut in enumerate(cuts):
+            _, below[k] = self.hist_below(thr, np.full(nl, cut), dirp)
+        return np.diff(below, axis=0).T
+
     def dz_medians(self, edges, dirp=None, thr_bits=None):
         """Per lag class: (count, median |dz|) exactly as np.nanmedian would return
         over the materialised lag class (estimators.py:178).

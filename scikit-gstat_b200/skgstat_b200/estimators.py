@@ -60,4 +60,39 @@ def finalize_dowd(count, median):
     return np.where(np.asarray(count) == 0, np.nan, 2.198 * m ** 2 / 2)
 
 
-ESTIMATORS = dict(matheron=matheron, cressie=cressie, dowd=dowd)
+def minmax(x):
+    """estimators.py:257-296."""
+    x = np.asarray(x, dtype=float)
+    return (np.nanmax(x) - np.nanmin(x)) / np.nanmean(x)
+
+
+def percentile(x, p=50):
+    """estimators.py:299-324."""
+    return np.percentile(np.asarray(x, dtype=float), q=p)
+
+
+def entropy(x, bins=None):
+    """estimators.py:327-367 + util/shannon.py:27-34."""
+    if bins is None:
+        bins = 15
+    c, _ = np.histogram(np.asarray(x, dtype=float), bins=bins)
+    return shannon_from_counts(c)
+
+
+def shannon_from_counts(c):
+    """util/shannon.py:30-34 on a histogram that already exists."""
+    c = np.asarray(c)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = c / np.sum(c) + 1e-15
+    return -np.fromiter(map(np.log2, p), dtype=float).dot(p)
+
+
+def finalize_minmax(count, vmin, vmax, total):
+    n = np.asarray(count, dtype=float)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = (np.asarray(vmax, dtype=float) - np.asarray(vmin, dtype=float)) / (np.asarray(total, dtype=float) / n)
+    return np.where(n == 0, np.nan, out)
+
+
+ESTIMATORS = dict(matheron=matheron, cressie=cressie, dowd=dowd, minmax=minmax,
+                  percentile=percentile, entropy=entropy)

@@ -73,3 +73,8 @@ def golden_kriging_ext():
 @pytest.fixture(scope="session")
 def golden_binners():
     return Golden("binners")
+
+
+@pytest.fixture(scope="session")
+def golden_estimators():
+    return Golden("estimators")
