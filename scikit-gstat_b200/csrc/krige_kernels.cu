@@ -130,7 +130,7 @@ __global__ void grid_sort_cells_kernel(const int* __restrict__ cell_start, int n
 // Modified Bessel function of the second kind K_nu(x), real nu >= 0, x > 0 (scipy.special.kv in
 // models.py:419-422).  Temme's series for x < 2, Steed's continued fraction CF2 above, upward
 // recurrence from |mu| <= 1/2 (the classical bessik scheme).
-__device__ double bessel_k(double nu, double x) {
+__device__ __noinline__ double bessel_k(double nu, double x) {
   const double EPS = 1e-16, PI = 3.141592653589793;
   const int nl = (int)(nu + 0.5);
   const double xmu = nu - nl, xmu2 = xmu * xmu;
@@ -199,15 +199,19 @@ __device__ double bessel_k(double nu, double x) {
   return rkmu;
 }
 
+// models.py:413-422; kept out of line so that the common models do not pay its registers
+__device__ __noinline__ double gamma_matern(double h, double a, double s, double b, double c0, double gnorm) {
+  if (h == 0.0) return b;
+  const double u = (h * sqrt(s)) / a;
+  const double kv = bessel_k(s, 2.0 * u);
+  if (kv == 0.0) return b + c0;  // K underflows far outside the range: gamma = sill
+  return b + c0 * (1.0 - gnorm * pow(u, s) * kv);
+}
+
 __device__ __forceinline__ double gamma_model(double h, const ModelParams& m) {
   switch (m.model) {
-    case SKG_MODEL_MATERN: {  // models.py:413-422
-      if (h == 0.0) return m.b;
-      const double u = (h * sqrt(m.s)) / m.a;
-      const double kv = bessel_k(m.s, 2.0 * u);
-      if (kv == 0.0) return m.b + m.c0;  // K underflows far outside the range: gamma = sill
-      return m.b + m.c0 * (1.0 - m.gnorm * pow(u, m.s) * kv);
-    }
+    case SKG_MODEL_MATERN:
+      return gamma_matern(h, m.a, m.s, m.b, m.c0, m.gnorm);
     case SKG_MODEL_SPHERICAL: {  // models.py:77-82
       if (h <= m.r) {
         const double q = h / m.a;
@@ -685,7 +689,7 @@ __device__ __forceinline__ int prow(int i, int n) {  // offset of packed row i (
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(104)
 krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -801,7 +805,7 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
         const int ok = k * (k + 1) / 2;
         const double akk = L[ok + k];
         if (!(akk > 0.0)) { bad = true; break; }
-        const double rd = 1.0 / sqrt(akk);
+        const double rd = rsqrt(akk);
         for (int i = k + 1 + lane; i < R; i += 32) {
           const int o = prow(i, n) + k;
           L[o] *= rd;
@@ -814,8 +818,11 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
             const int o = prow(i, n);
             const double li = L[o + k];
             const int cmax = i < n ? min(i, ke - 1) : ke - 1;
-            for (int c = k + 1; c <= cmax; ++c)
-              L[o + c] = fma(-li, L[c * (c + 1) / 2 + k], L[o + c]);
+            int oc = (k + 1) * (k + 2) / 2 + k;   // offset of L[c][k], advanced by c + 1 per column
+            for (int c = k + 1; c <= cmax; ++c) {
+              L[o + c] = fma(-li, L[oc], L[o + c]);
+              oc += c + 1;
+            }
           }
         }
         __syncwarp();
