@@ -349,6 +349,7 @@ int skg_pair_hist_batch(const double* coords, const double* values, int n_vector
   std::memcpy(&win.hi[0], &thr_bits[n_lags - 1], 8);
   const int64_t ntl = (tile_end - tile_begin + tile_stride - 1) / tile_stride;
   const int js = choose_js(ntl);
+  cull_set_dir(&win, dp);
   rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, js, S, st);  // once per call
   if (rc) return rc;
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);

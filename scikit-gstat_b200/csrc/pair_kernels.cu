@@ -177,6 +177,9 @@ __global__ void item_flags_kernel(const double* __restrict__ bbox, const double*
         const double lo = a * (1.0 - 1e-12), hi = b * (1.0 + 1e-12);
         for (int w = 0; w < win.count; ++w) keep |= (lo < win.hi[w] && hi >= win.lo[w]) ? 1 : 0;
         if (win.want_max && hi >= need) keep = 1;
+        if (DIM == 2 && keep && win.dir_model != SKG_DIR_NONE &&
+            !dir_box_may_pass(bbox + (int64_t)I * 6, jb, win))
+          keep = 0;
       }
     }
     flags[k] = (unsigned char)keep;
@@ -662,6 +665,7 @@ static int select_common(bool gather, const double* coords, const double* values
                  !gather && n_lags <= 0 && max_bits != nullptr, &win);
   const int64_t ntiles = (t1 - t0 + stride - 1) / stride;
   const int js = choose_js(ntiles);
+  cull_set_dir(&win, dp);
   rc = launch_cull(coords, n, dim, win, t0, t1, stride, js, S, st);
   if (rc) return rc;
   // chunk/warp-level culling inside the sweep uses the hull of all windows (and
@@ -740,6 +744,7 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
   win.hi[0] = bits_to_double(thr_bits[n_lags - 1]);
   const int64_t ntl = (tile_end - tile_begin + tile_stride - 1) / tile_stride;
   const int js = choose_js(ntl);
+  cull_set_dir(&win, dp);
   rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, js, S, st);
   if (rc) return rc;
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);

@@ -23,7 +23,43 @@ struct CullWindows {
   int want_max;    // also keep tiles that can hold the maximum squared distance
   double lo[64];   // inclusive
   double hi[64];   // exclusive
+  // directional mask (0 = none): work items whose box of difference vectors cannot meet the
+  // azimuth cone / bandwidth strip are dropped as well (conservative, hence exact)
+  int dir_model, dir_tol_all;
+  double cos_az, sin_az, tan_ht, half_bw;
 };
+
+inline void cull_set_dir(CullWindows* w, const DirParams& dp) {
+  w->dir_model = dp.model;
+  w->dir_tol_all = dp.tol_all;
+  w->cos_az = dp.cos_az; w->sin_az = dp.sin_az; w->tan_ht = dp.tan_ht; w->half_bw = dp.half_bw;
+}
+
+// Can any difference vector P_i - P_j between the two boxes pass the directional mask?
+// dot = dx cos - dy sin and crs = dx sin + dy cos (dir_fast) are linear in (dx, dy), so their
+// ranges over the rectangle of difference vectors come from its corners; the mask needs
+// |crs| <= tan(tol/2) |dot| (and |crs| <= bandwidth/2 for the triangle).
+__device__ __forceinline__ bool dir_box_may_pass(const double* ibox, const double* jbox,
+                                                 const CullWindows& w) {
+  const double dx0 = ibox[0] - jbox[3], dx1 = ibox[3] - jbox[0];
+  const double dy0 = ibox[1] - jbox[4], dy1 = ibox[4] - jbox[1];
+  double dmin = 1e300, dmax = -1e300, cmin = 1e300, cmax = -1e300;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double dx = (k & 1) ? dx1 : dx0, dy = (k & 2) ? dy1 : dy0;
+    const double dot = dx * w.cos_az - dy * w.sin_az;
+    const double crs = dx * w.sin_az + dy * w.cos_az;
+    dmin = fmin(dmin, dot); dmax = fmax(dmax, dot);
+    cmin = fmin(cmin, crs); cmax = fmax(cmax, crs);
+  }
+  if (!(dmin == dmin && cmin == cmin)) return true;  // NaN boxes: keep
+  const double dot_hi = fmax(fabs(dmin), fabs(dmax));
+  const double crs_lo = (cmin <= 0.0 && cmax >= 0.0) ? 0.0 : fmin(fabs(cmin), fabs(cmax));
+  const double slack = 1e-9 * (fabs(dx0) + fabs(dx1) + fabs(dy0) + fabs(dy1));
+  if (!w.dir_tol_all && crs_lo > w.tan_ht * dot_hi + slack) return false;
+  if (w.dir_model == SKG_DIR_TRIANGLE && crs_lo > w.half_bw + slack) return false;
+  return true;
+}
 
 struct SweepScratch {  // views into the caller's scratch buffer
   unsigned long long* counters;  // [0] = number of listed tiles
