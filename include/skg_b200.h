@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SKG_ABI_VERSION 3
+#define SKG_ABI_VERSION 4
 #define SKG_TILE 256            /* points per tile edge                          */
 #define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
 #define SKG_KRIGE_MAX_POINTS 64 /* max_points supported by the warp-per-target kernel */
@@ -138,9 +138,12 @@ int64_t skg_pair_num_tiles(int64_t n);
  *   dir[4] = 1: such pairs FAIL the mask in every kernel; the caller lists them
  *               once with skg_pair_dir_ambiguous, decides them with the literal
  *               numpy formula on the host (the reference's own arithmetic) and
- *               adds their contributions.  This is what skgstat_b200 does. */
+ *               adds their contributions.  This is what skgstat_b200 does.
+ *   scratch [dev] or NULL: >= skg_pair_scratch_bytes(n, 1) bytes lets the call sweep only the
+ *   tiles whose difference vectors can come near the mask boundary (Z-order sorted points). */
 int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const double* dir,
                            int32_t* pair_i, int32_t* pair_j, uint64_t* count, int64_t capacity,
+                           void* scratch, int64_t scratch_bytes,
                            int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* K2 - fused distance -> lag class -> estimator statistics.

@@ -122,8 +122,11 @@ pair_hist_batch_kernel(const double* __restrict__ coords, const double* __restri
 #pragma unroll
       for (int r = 0; r < HR; ++r) {
         double a, b;
-        subblock_range<DIM>(bbox32, (int64_t)I * 8 + r * (HB / 32) + (tid >> 5), jb, a, b);
-        wact |= (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+        const int64_t sub = (int64_t)I * 8 + r * (HB / 32) + (tid >> 5);
+        subblock_range<DIM>(bbox32, sub, jb, a, b);
+        bool on = (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+        if (DIR && DIM == 2 && on) on = dir_box_may_pass(bbox32 + sub * 6, jb, dp);
+        wact |= on;
       }
     }
     const int64_t jn = n - ((int64_t)J * TILE + jbeg);

@@ -37,7 +37,9 @@ template <int DIM, class Op>
 __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
                                             const double* __restrict__ values, int64_t n,
                                             int64_t t0, int64_t t1, int64_t stride,
-                                            TileSmem<DIM>& sm, Op& op) {
+                                            TileSmem<DIM>& sm, Op& op,
+                                            const unsigned int* __restrict__ tile_list = nullptr,
+                                            const unsigned long long* __restrict__ tile_count = nullptr) {
   const int tid = threadIdx.x;
   const int64_t nt = (n + TILE - 1) / TILE;
   const double qnan = __longlong_as_double(NAN_BITS);
@@ -45,7 +47,17 @@ __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
   const double* __restrict__ Y = coords + n;
   const double* __restrict__ W = coords + 2 * n;
 
-  for (int64_t t = t0 + (int64_t)blockIdx.x * stride; t < t1; t += (int64_t)gridDim.x * stride) {
+  // with a tile list (culling prelude, one work item per tile) only the listed tiles are swept
+  const int64_t nlist = tile_list ? (int64_t)(*tile_count) : 0;
+  for (int64_t w = blockIdx.x;; w += gridDim.x) {
+    int64_t t;
+    if (tile_list) {
+      if (w >= nlist) break;
+      t = tile_list[w];
+    } else {
+      t = t0 + w * stride;
+      if (t >= t1) break;
+    }
     int I, J;
     tile_decode(t, nt, I, J);
     double xi[RI], yi[RI], wi[RI], zi[RI];
@@ -296,11 +308,13 @@ __global__ void __launch_bounds__(BLOCK)
 pair_dir_ambiguous_kernel(const double* __restrict__ coords, int64_t n,
                           const __grid_constant__ DirParams dp, int* __restrict__ out_i,
                           int* __restrict__ out_j, unsigned long long* __restrict__ count,
-                          long long capacity, int64_t t0, int64_t t1, int64_t stride) {
+                          long long capacity, int64_t t0, int64_t t1, int64_t stride,
+                          const unsigned int* __restrict__ tile_list,
+                          const unsigned long long* __restrict__ tile_count) {
   __shared__ TileSmem<2> sm;
   AmbOp op;
   op.dp = &dp; op.out_i = out_i; op.out_j = out_j; op.count = count; op.capacity = capacity;
-  sweep_tiles<2>(coords, nullptr, n, t0, t1, stride, sm, op);
+  sweep_tiles<2>(coords, nullptr, n, t0, t1, stride, sm, op, tile_list, tile_count);
 }
 
 // ------------------------------------------------------- materialisation ---
@@ -808,6 +822,7 @@ int skg_pair_select_gather(const double* coords, const double* values, int n_val
 
 int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const double* dir,
                            int32_t* pair_i, int32_t* pair_j, uint64_t* count, int64_t capacity,
+                           void* scratch, int64_t scratch_bytes,
                            int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream) {
   int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
@@ -821,9 +836,26 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ntl = (tile_end - tile_begin + tile_stride - 1) / tile_stride;
   const int64_t grid = std::min<int64_t>((int64_t)sm_count() * MAX_GRID_PER_SM, ntl);
+  const unsigned int* list = nullptr;
+  const unsigned long long* list_count = nullptr;
+  if (scratch) {  // optional: only the tiles whose difference vectors can come near the mask boundary
+    SweepScratch S;
+    rc = carve_scratch(scratch, scratch_bytes, n, 0, &S);
+    if (rc) return rc;
+    CullWindows win;
+    std::memset(&win, 0, sizeof(win));
+    win.count = 1;
+    win.lo[0] = 0.0;
+    win.hi[0] = bits_to_double(INF_BITS);
+    cull_set_dir(&win, dp);
+    rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, 1, S, st);
+    if (rc) return rc;
+    list = S.list;
+    list_count = S.counters;
+  }
   pair_dir_ambiguous_kernel<<<(unsigned)grid, BLOCK, 0, st>>>(
       coords, n, dp, pair_i, pair_j, reinterpret_cast<unsigned long long*>(count),
-      (long long)capacity, tile_begin, tile_end, tile_stride);
+      (long long)capacity, tile_begin, tile_end, tile_stride, list, list_count);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,12 +35,22 @@ inline void cull_set_dir(CullWindows* w, const DirParams& dp) {
   w->cos_az = dp.cos_az; w->sin_az = dp.sin_az; w->tan_ht = dp.tan_ht; w->half_bw = dp.half_bw;
 }
 
+template <class W> struct DirView;  // uniform access to the direction fields of CullWindows / DirParams
+template <> struct DirView<CullWindows> {
+  static __device__ __forceinline__ int model(const CullWindows& w) { return w.dir_model; }
+  static __device__ __forceinline__ int tol_all(const CullWindows& w) { return w.dir_tol_all; }
+};
+template <> struct DirView<DirParams> {
+  static __device__ __forceinline__ int model(const DirParams& w) { return w.model; }
+  static __device__ __forceinline__ int tol_all(const DirParams& w) { return w.tol_all; }
+};
+
 // Can any difference vector P_i - P_j between the two boxes pass the directional mask?
 // dot = dx cos - dy sin and crs = dx sin + dy cos (dir_fast) are linear in (dx, dy), so their
 // ranges over the rectangle of difference vectors come from its corners; the mask needs
 // |crs| <= tan(tol/2) |dot| (and |crs| <= bandwidth/2 for the triangle).
-__device__ __forceinline__ bool dir_box_may_pass(const double* ibox, const double* jbox,
-                                                 const CullWindows& w) {
+template <class W>
+__device__ __forceinline__ bool dir_box_may_pass(const double* ibox, const double* jbox, const W& w) {
   const double dx0 = ibox[0] - jbox[3], dx1 = ibox[3] - jbox[0];
   const double dy0 = ibox[1] - jbox[4], dy1 = ibox[4] - jbox[1];
   double dmin = 1e300, dmax = -1e300, cmin = 1e300, cmax = -1e300;
@@ -56,8 +66,8 @@ __device__ __forceinline__ bool dir_box_may_pass(const double* ibox, const doubl
   const double dot_hi = fmax(fabs(dmin), fabs(dmax));
   const double crs_lo = (cmin <= 0.0 && cmax >= 0.0) ? 0.0 : fmin(fabs(cmin), fabs(cmax));
   const double slack = 1e-9 * (fabs(dx0) + fabs(dx1) + fabs(dy0) + fabs(dy1));
-  if (!w.dir_tol_all && crs_lo > w.tan_ht * dot_hi + slack) return false;
-  if (w.dir_model == SKG_DIR_TRIANGLE && crs_lo > w.half_bw + slack) return false;
+  if (!DirView<W>::tol_all(w) && crs_lo > w.tan_ht * dot_hi + slack) return false;
+  if (DirView<W>::model(w) == SKG_DIR_TRIANGLE && crs_lo > w.half_bw + slack) return false;
   return true;
 }
 
@@ -372,8 +382,11 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
 #pragma unroll
       for (int r = 0; r < HR; ++r) {
         double a, b;
-        subblock_range<DIM>(bbox32, (int64_t)I * 8 + r * (HB / 32) + (tid >> 5), jb, a, b);
-        wact |= (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+        const int64_t sub = (int64_t)I * 8 + r * (HB / 32) + (tid >> 5);
+        subblock_range<DIM>(bbox32, sub, jb, a, b);
+        bool on = (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+        if (DIR && DIM == 2 && on) on = dir_box_may_pass(bbox32 + sub * 6, jb, dp);
+        wact |= on;
       }
     }
     const int64_t jn = n - ((int64_t)J * TILE + jbeg);
@@ -583,8 +596,11 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
 #pragma unroll
       for (int r = 0; r < HR; ++r) {
         double a, b;
-        subblock_range<DIM>(bbox32, (int64_t)I * 8 + r * (HB / 32) + (tid >> 5), jb, a, b);
-        wact |= (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+        const int64_t sub = (int64_t)I * 8 + r * (HB / 32) + (tid >> 5);
+        subblock_range<DIM>(bbox32, sub, jb, a, b);
+        bool on = (a * (1.0 - 1e-12) < whi && b * (1.0 + 1e-12) >= wlo);
+        if (DIR && DIM == 2 && on) on = dir_box_may_pass(bbox32 + sub * 6, jb, dp);
+        wact |= on;
       }
     }
     const int64_t jn = n - ((int64_t)J * TILE + jbeg);

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libskg_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TILE = 256
 MAX_LAGS = 250
 KRIGE_MAX_POINTS = 64
@@ -40,7 +40,7 @@ SIGNATURES = {
     "skg_fp64_peak": (_int, [_int, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "skg_morton_keys": (_int, [_p, _i64, _int, _p, _p, _p, _p]),
     "skg_pair_num_tiles": (_i64, [_i64]),
-    "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
+    "skg_pair_dir_ambiguous": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_scratch_bytes": (_i64, [_i64, _int]),
     "skg_pair_hist": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _i64,
                              _i64, _i64, _i64, _p]),

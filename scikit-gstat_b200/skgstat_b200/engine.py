@@ -299,11 +299,12 @@ class PairEngine:
         pj = torch.empty(cap, dtype=torch.int32, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
+            scratch = self._hist_scratch(1)
             rc = self.lib.skg_pair_dir_ambiguous(
                 _ptr(self.coords), self.n, self.dim, _hptr(dirp), _ptr(pi), _ptr(pj), _ptr(cnt),
-                cap, t0, t1, ts, self._stream())
+                cap, _ptr(scratch), scratch.numel(), t0, t1, ts, self._stream())
         _lib.check(rc, "skg_pair_dir_ambiguous")
-        self.launches += 1 if t1 > t0 else 0
+        self.launches += 4 if t1 > t0 else 0
         got = int(cnt.item())
         if got > cap:
             raise RuntimeError(
