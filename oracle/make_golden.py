@@ -465,6 +465,56 @@ def make_estimators(skg, ds):
     print("estimator cases:", len(manifest))
 
 
+def make_sparse(skg, ds):
+    """MetricSpace(max_dist=...) - only pairs with 0 < d <= max_dist exist
+    (MetricSpace.py:141-147, Variogram.py:1202-1227, 1910-1936)."""
+    arrays, manifest = {}, []
+    sets = dict(ds)
+    c, v = ds["rnd400"]
+    cd = c.copy()
+    cd[7] = cd[3]
+    cd[100] = cd[3]          # coincident points: the sparse matrix drops their zero distances
+    sets["rnd400dup"] = (cd, v)
+    # the sparse branch of _format_values_stack subtracts in the values' own dtype (uint8 pancake
+    # values wrap around there, unlike the dense pdist branch): use float observations
+    sets["pancake300"] = (ds["pancake300"][0], np.asarray(ds["pancake300"][1], dtype=float))
+    cfgs = [("rnd400", 30.0), ("rnd400", 61.5), ("rnd400dup", 45.0), ("pancake300", 150.0),
+            ("lattice225", 5.0), ("rnd3d150", 22.0)]
+    for dname, md in cfgs:
+        c, v = sets[dname]
+        arrays["in/%s/coords" % dname] = c
+        arrays["in/%s/values" % dname] = v
+        for est, bf, n_lags, ml in (("matheron", "even", 10, None), ("cressie", "uniform", 8, "median"),
+                                    ("dowd", "even", 12, 0.5), ("matheron", "sturges", 10, None),
+                                    ("matheron", "fd", 10, "median"), ("minmax", "even", 6, None),
+                                    ("matheron", "even", 10, "mean"), ("matheron", "even", 8, md * 1.7)):
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    ms = skg.MetricSpace(c, max_dist=md)
+                    V = skg.Variogram(ms, v, estimator=est, bin_func=bf, n_lags=n_lags, maxlag=ml,
+                                      fit_method=None)
+                    key = "x/%d" % len(manifest)
+                    out = dict(bins=V.bins, bin_count=np.asarray(V.bin_count, dtype=np.int64),
+                               experimental=V.experimental,
+                               maxlag=np.array(np.nan if V.maxlag is None else V.maxlag, dtype=float))
+                    if est == "matheron" and bf == "even" and ml is None:
+                        out["distance"] = V.distance
+                        out["diffs"] = V.pairwise_diffs
+            except Exception as e:   # e.g. minmax on an empty lag class raises in the reference
+                print("skip", dname, md, est, bf, ml, type(e).__name__)
+                continue
+            for k2, v2 in out.items():
+                arrays[key + "/" + k2] = v2
+            manifest.append(dict(key=key, kind="variogram", dataset=dname, max_dist=md, estimator=est,
+                                 bin_func=bf, n_lags=n_lags, maxlag=ml))
+    # (DirectionalVariogram cannot take a MetricSpace in the reference: DirectionalVariogram.py:245
+    #  reads self.dist_func before it exists)
+    arrays["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(OUT, "sparse.npz"), **arrays)
+    print("sparse cases:", len(manifest))
+
+
 def make_api_fixture(skg):
     """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
     test_variogram.py::test_fit_lm; data only."""
@@ -478,7 +528,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners", "estimators"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners", "estimators", "sparse"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -497,6 +547,8 @@ def main():
         make_binners(skg, ds)
     if "estimators" in which:
         make_estimators(skg, ds)
+    if "sparse" in which:
+        make_sparse(skg, ds)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,8 @@ everything downstream reads it; here the pair kernels work from the coordinates
 directly and ``dists`` only exists as a lazily materialised accessor (produced by
 skg_pair_materialize, bit-identical to scipy's pdist/squareform).
 
-Out of scope: ``max_dist`` sparse spaces,
+``max_dist`` gives the reference's sparse semantics (only pairs with 0 < d <= max_dist exist)
+through a pair filter on the engine.  Out of scope:
 non-euclidean metrics, Probabalistic/RasterEquidistant samplers - they raise
 NotImplementedError instead of silently taking another path.
 """
@@ -20,8 +21,6 @@ class MetricSpace:
         if dist_metric != "euclidean":
             raise NotImplementedError(
                 "skgstat_b200 implements the euclidean metric only (got %r)" % (dist_metric,))
-        if max_dist is not None:
-            raise NotImplementedError("sparse MetricSpace (max_dist) is out of scope")
         c = np.asarray(coords)
         if c.ndim != 2:
             raise ValueError("coords has to be of shape (Npoints, Ndim)")
@@ -39,6 +38,8 @@ class MetricSpace:
         if self._engine is None or self._engine.group is not group:
             from .engine import PairEngine
             self._engine = PairEngine(self.coords, group=group)
+            # sparse space (MetricSpace.py:141-147): only pairs with 0 < d <= max_dist exist
+            self._engine.set_pair_filter(self.max_dist)
             self._cache = {}
         return self._engine
 
@@ -50,7 +51,18 @@ class MetricSpace:
 
     @property
     def dists(self):
-        """Dense N x N distance matrix (materialising accessor)."""
+        """N x N distance matrix (materialising accessor): dense, or - with max_dist - the
+        scipy.sparse CSR matrix of the pairs with 0 < d <= max_dist (MetricSpace.py:141-147)."""
+        if self._dists is None and self.max_dist is not None:
+            from scipy import sparse
+            eng = self.engine()
+            d = eng.materialize(("dist",), _raw=True)["dist"]
+            keep = np.flatnonzero((d > 0) & (d <= self.max_dist))
+            iu, ju = np.triu_indices(len(self), 1)
+            i, j, v = iu[keep], ju[keep], d[keep]
+            m = sparse.coo_matrix((np.concatenate((v, v)), (np.concatenate((i, j)), np.concatenate((j, i)))),
+                                  shape=(len(self), len(self)))
+            self._dists = m.tocsr()
         if self._dists is None:
             from scipy.spatial.distance import squareform  # layout helper only
             d = self.engine().materialize(("dist",))["dist"]

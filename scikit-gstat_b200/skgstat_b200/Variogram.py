@@ -20,7 +20,7 @@ device on demand.  The model fit is scipy ``curve_fit`` on n_lags points and
 stays on the CPU, as in the reference (Variogram.py:1584-1821).
 
 Out of scope, raising NotImplementedError rather than taking a slow path:
-``samples=`` (ProbabalisticMetricSpace), sparse ``max_dist`` spaces, non-euclidean
+``samples=`` (ProbabalisticMetricSpace), non-euclidean
 metrics, cross/aggregate (2-D ``values``) variograms, clustering / histogram-rule
 binners, the genton/minmax/percentile/entropy estimators by name, ``fit_method='ml'``
 and harmonised models.

@@ -159,6 +159,8 @@ class PairEngine:
             self.t0 = self.t1 = 0
         self._scratch = None
         self._all_finite = None
+        self.pair_filter = None  # (exclusive upper bound of s as bits, drop s == 0): sparse max_dist spaces
+        self.max_dist = None
         self._buffers = {}
         self._amb_cache = {}
         self.n_ambiguous = 0
@@ -273,6 +275,46 @@ class PairEngine:
         js = max(int(c[2]), 1)
         return int(c[0]), int(c[3]), _lib.TILE * (_lib.TILE // js)
 
+    # ---------------------------------------------- sparse (max_dist) spaces
+    def set_pair_filter(self, max_dist):
+        """MetricSpace(max_dist=...) semantics (MetricSpace.py:141-147, Variogram.py:1210-1227): only
+        pairs with 0 < d <= max_dist exist (the reference's sparse matrix drops coincident points).
+        Every sweep then works on lag thresholds clipped to that range, see _filter_thr."""
+        from ._exact import sq_upper_inclusive_bits
+        self.max_dist = None if max_dist is None else float(max_dist)
+        self.pair_filter = None if max_dist is None else (int(sq_upper_inclusive_bits(float(max_dist))), True)
+
+    def _filter_thr(self, thr):
+        """thr (bit patterns of the lag thresholds) -> (thr2, src): thr2 adds a leading class for
+        s == 0 (discarded) and clips at the filter's upper bound; src[k] = class of thr2 that
+        holds user class k, or -1 when the class lies entirely beyond the bound."""
+        if self.pair_filter is None:
+            return thr, None
+        hi, drop_zero = self.pair_filter
+        out = [1] if drop_zero else []
+        src = np.full(thr.size, -1, dtype=np.int64)
+        lower = 0
+        for k in range(thr.size):
+            if lower < hi:
+                src[k] = len(out)
+                out.append(min(int(thr[k]), hi))
+            lower = int(thr[k])
+        thr2 = np.array(out, dtype=np.uint64)
+        if thr2.size > _lib.MAX_LAGS:
+            raise ValueError("too many lag classes for a sparse (max_dist) space")
+        return thr2, src
+
+    @staticmethod
+    def _unmap(arr2, src, fill=0):
+        """Per-class results of the filtered thresholds back to the user's classes."""
+        if src is None:
+            return arr2
+        arr2 = np.asarray(arr2)
+        out = np.full((src.size,) + arr2.shape[1:], fill, dtype=arr2.dtype if fill == 0 else np.float64)
+        ok = src >= 0
+        out[ok] = arr2[src[ok]]
+        return out
+
     def sq_upper_bound(self) -> float:
         """A value >= every squared pair distance (bounding-box diagonal, padded)."""
         ct = np.ascontiguousarray(self._orig_coords.T)
@@ -346,6 +388,7 @@ class PairEngine:
         if self.values is None:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        thr, fsrc = self._filter_thr(thr)
         nl = int(thr.size)
         out = self._buffer("hist_out", 3 * nl, torch.float64).zero_()
         cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
@@ -372,7 +415,8 @@ class PairEngine:
             out += to_device(extra, self.device)
         D.allreduce_sum_(out, self.group)  # the single collective of the fused pass
         host = to_host(out)
-        return host[:nl].astype(np.int64), host[nl:2 * nl].copy(), host[2 * nl:].copy()
+        return (self._unmap(host[:nl].astype(np.int64), fsrc), self._unmap(host[nl:2 * nl].copy(), fsrc),
+                self._unmap(host[2 * nl:].copy(), fsrc))
 
     def dist_moments(self, limit: float, dirp=None, third: bool = True):
         """(n, sum d, sum d^2, sum d^3) over the (mask-passing) pairs with d <= limit: the
@@ -380,29 +424,34 @@ class PairEngine:
         Fused-pass sweeps whose "value difference" is a power of the distance (SKG_VALUE_DIST_*)."""
         from ._exact import sq_upper_inclusive_bits
         thr = np.array([sq_upper_inclusive_bits(limit)], dtype=np.uint64)  # class 0: d <= limit
+        thr, fsrc = self._filter_thr(thr)
+        cls = 0 if fsrc is None else int(fsrc[0])   # the class that holds 0 < d <= limit
+        ncl = int(thr.size)
         amb = self.ambiguous_pairs(dirp)
 
         def sweep(mode, stats):
-            out = self._buffer("hist_out", 3, torch.float64).zero_()
-            cnt = self._buffer("hist_cnt", 1, torch.int64).zero_()
-            scratch = self._hist_scratch(1)
+            out = self._buffer("hist_out", 3 * ncl, torch.float64).zero_()
+            cnt = self._buffer("hist_cnt", ncl, torch.int64).zero_()
+            scratch = self._hist_scratch(ncl)
             with torch.cuda.device(self.device):
                 rc = self.lib.skg_pair_hist(
-                    _ptr(self.coords), None, 0, mode, self.n, self.dim, _hptr(dirp), _hptr(thr), 1,
-                    int(stats), None, _ptr(cnt), _ptr(out[1:2]), _ptr(out[2:3]), _ptr(scratch),
+                    _ptr(self.coords), None, 0, mode, self.n, self.dim, _hptr(dirp), _hptr(thr), ncl,
+                    int(stats), None, _ptr(cnt), _ptr(out[ncl:2 * ncl]), _ptr(out[2 * ncl:]), _ptr(scratch),
                     scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
             _lib.check(rc, "skg_pair_hist")
             self.launches += 5 if self.t1 > self.t0 else 0
-            out[:1] = cnt.to(torch.float64)
+            out[:ncl] = cnt.to(torch.float64)
             if amb is not None and amb[0].size:
                 s_bits, _ = self._amb_keys(amb)
-                sv = s_bits[s_bits < thr[0]].view(np.float64)
+                sv = s_bits[(s_bits < thr[cls]) & (s_bits >= (thr[cls - 1] if cls else 0))].view(np.float64)
                 d = np.sqrt(sv)
                 val = {_lib.VALUE_DIST_S: sv, _lib.VALUE_DIST_D: d, _lib.VALUE_DIST_D15: d * np.sqrt(d)}[mode]
-                extra = np.array([sv.size, float(np.sum(val * val)), float(np.sum(np.sqrt(val)))])
+                extra = np.zeros(3 * ncl)
+                extra[cls], extra[ncl + cls], extra[2 * ncl + cls] = sv.size, float(np.sum(val * val)), float(np.sum(np.sqrt(val)))
                 out += to_device(extra, self.device)
             D.allreduce_sum_(out, self.group)
-            return to_host(out)
+            h = to_host(out)
+            return np.array([h[cls], h[ncl + cls], h[2 * ncl + cls]])
 
         a = sweep(_lib.VALUE_DIST_S, _lib.STAT_SUM_SQ | _lib.STAT_SUM_SQRT)   # sum d^4, sum d
         b = sweep(_lib.VALUE_DIST_D, _lib.STAT_SUM_SQ)                        # sum d^2
@@ -424,6 +473,7 @@ class PairEngine:
         if stat not in (_lib.STAT_SUM_SQ, _lib.STAT_SUM_SQRT):
             raise ValueError("stat must be STAT_SUM_SQ or STAT_SUM_SQRT")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        thr, fsrc = self._filter_thr(thr)
         nl = int(thr.size)
         K = int(V.shape[0])
         if nl > self.lib.skg_pair_batch_max_lags():
@@ -468,7 +518,9 @@ class PairEngine:
             if counts is None:
                 counts = host[0].astype(np.int64)
             sums[k0:k1] = host[1:]
-        return counts, sums
+        if fsrc is not None:
+            sums = self._unmap(sums.T, fsrc).T
+        return self._unmap(counts, fsrc), np.ascontiguousarray(sums)
 
     # ------------------------------------------------ K1/K3 (order statistics)
     def _select_runner(self, key_kind, thr, dirp, n_buckets, collect_max=None):
@@ -577,6 +629,7 @@ class PairEngine:
             return None
         idx = np.sort(np.random.default_rng(54321).choice(self.n, size=m, replace=False))
         sub = PairEngine(self._orig_coords[idx], device=self.device)
+        sub.pair_filter = self.pair_filter
         # fractions of the wanted ranks; the totals are proportional up to sampling noise
         probe = rank_fn(10 ** 9)
         if not probe or len(probe) > 12:
@@ -612,6 +665,7 @@ class PairEngine:
         """Exact pair counts per class of squared distance for bit-pattern thresholds
         `thr` (skg_pair_hist with no estimator statistic: private counters, no atomics).
         No values needed; all-reduced over the group."""
+        thr, fsrc = self._filter_thr(np.asarray(thr, np.uint64))
         nl = int(thr.size)
         cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
         scratch = self._hist_scratch(nl)
@@ -630,7 +684,7 @@ class PairEngine:
             extra = np.bincount(g[g < nl], minlength=nl).astype(np.int64)
             cnt += to_device(extra, self.device)
         D.allreduce_sum_(cnt, self.group)
-        return to_host(cnt).astype(np.int64)
+        return self._unmap(to_host(cnt).astype(np.int64), fsrc)
 
     def sq_order_stats(self, rank_fn, dirp=None, limit: Optional[float] = None):
         """Exact order statistics of the squared distances s of all (mask-passing)
@@ -646,6 +700,10 @@ class PairEngine:
         hi_bits = to_bits(ub) + 1
         if limit is not None:
             hi_bits = min(hi_bits, sq_upper_inclusive_bits(limit))
+        zero_lo = 0
+        if self.pair_filter is not None:          # sparse space: 0 < d <= max_dist only
+            hi_bits = min(hi_bits, self.pair_filter[0])
+            zero_lo = 1 if self.pair_filter[1] else 0
         hi_val = from_bits(hi_bits)
 
         def default_classes():
@@ -658,7 +716,7 @@ class PairEngine:
         # without mask, limit or NaN coordinates the number of keys is known: the counting
         # sweep can then stop at the last window and cull everything beyond it
         known_total = None
-        if dirp is None and limit is None:
+        if dirp is None and limit is None and self.pair_filter is None:
             if self._all_finite is None:
                 self._all_finite = bool(np.isfinite(self._orig_coords).all())
             if self._all_finite:
@@ -690,7 +748,7 @@ class PairEngine:
         # window table: [lo_1, hi_1, lo_2, hi_2, ...]; class 2w+1 = inside window w
         bounds, win_lo, win_hi, base = [], [], [], []
         for c in wanted:
-            lo = int(thr[c - 1]) if c > 0 else 0
+            lo = int(thr[c - 1]) if c > 0 else zero_lo
             hi = int(thr[c])
             bounds += [lo, hi]
             win_lo.append(lo)
@@ -727,6 +785,9 @@ class PairEngine:
     def sq_max(self, dirp=None):
         """Largest squared distance among the (mask-passing) pairs (None if no pair
         passes): one sweep with an empty histogram window, i.e. no atomics."""
+        if self.pair_filter is not None:          # sparse space: the largest s inside the filter
+            vals, total = self.sq_order_stats(lambda t: [t - 1] if t else [], dirp=dirp)
+            return vals[total - 1] if total else None
         mx = torch.zeros(1, dtype=torch.int64, device=self.device)
         hist = torch.zeros(1, dtype=torch.int64, device=self.device)
         scratch = self._hist_scratch(1)
@@ -763,6 +824,12 @@ class PairEngine:
     def hist_below(self, thr: np.ndarray, dz_lo: np.ndarray, dirp=None):
         """Exact per-lag (pair count, count of pairs with |dz| < dz_lo[lag]) with the fused-pass
         kernel (private counters, no atomics); all-reduced over the group."""
+        thr, fsrc = self._filter_thr(np.asarray(thr, np.uint64))
+        if fsrc is not None:   # per-lag bounds follow their classes; the s == 0 class gets 0
+            lo2 = np.zeros(thr.size)
+            ok = fsrc >= 0
+            lo2[fsrc[ok]] = np.asarray(dz_lo, dtype=np.float64)[ok]
+            dz_lo = lo2
         nl = int(thr.size)
         cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
         below = self._buffer("hist_below", nl, torch.float64).zero_()
@@ -787,7 +854,7 @@ class PairEngine:
             both += to_device(extra, self.device)
         D.allreduce_sum_(both, self.group)
         host = to_host(both)
-        return host[:nl].astype(np.int64), host[nl:].astype(np.int64)
+        return self._unmap(host[:nl].astype(np.int64), fsrc), self._unmap(host[nl:].astype(np.int64), fsrc)
 
     def dz_abs_sums(self, edges, dirp=None, thr_bits=None):
         """Per lag class (count, sum of the pair differences): fused pass over the SQUARED
@@ -795,6 +862,7 @@ class PairEngine:
         if self.values is None:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        thr, fsrc = self._filter_thr(thr)
         nl = int(thr.size)
         out = self._buffer("hist_out", 3 * nl, torch.float64).zero_()
         cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
@@ -819,7 +887,7 @@ class PairEngine:
             out += to_device(extra, self.device)
         D.allreduce_sum_(out, self.group)
         host = to_host(out)
-        return host[:nl].astype(np.int64), host[2 * nl:].copy()
+        return self._unmap(host[:nl].astype(np.int64), fsrc), self._unmap(host[2 * nl:].copy(), fsrc)
 
     def dz_order_stats(self, edges, rank_fn, dirp=None, thr_bits=None):
         """Exact order statistics of the pair differences per lag class: rank_fn(lag, total) ->
@@ -827,9 +895,17 @@ class PairEngine:
         if self.values is None:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        thr, fsrc = self._filter_thr(thr)
         nl = int(thr.size)
         hi = to_bits(self._dz_bound) + 1
-        return self._dz_select(thr, dirp, [0] * nl, [hi] * nl, rank_fn)
+        if fsrc is None:
+            return self._dz_select(thr, dirp, [0] * nl, [hi] * nl, rank_fn)
+        back = {int(c): k for k, c in enumerate(fsrc) if c >= 0}   # filtered class -> user class
+        vals2, tot2 = self._dz_select(thr, dirp, [0] * nl, [hi] * nl,
+                                      lambda g, t: rank_fn(back[g], t) if g in back else [])
+        vals = [vals2[c] if c >= 0 else {} for c in fsrc]
+        tots = [tot2[c] if c >= 0 else 0 for c in fsrc]
+        return vals, tots
 
     def dz_value_histogram(self, edges, value_edges, dirp=None, thr_bits=None):
         """np.histogram(|dz| of lag class g, bins=value_edges)[0] for every lag class g: exact
@@ -860,6 +936,7 @@ class PairEngine:
         if self.values is None:
             raise ValueError("values not set")
         thr = sq_threshold_bits(edges) if thr_bits is None else np.asarray(thr_bits, np.uint64)
+        thr, fsrc = self._filter_thr(thr)
         nl = int(thr.size)
         hi = to_bits(self._dz_bound) + 1  # >= every pair's difference
 
@@ -911,7 +988,7 @@ class PairEngine:
                 a, b = med_lo[g], med_hi[g]
                 # np.median: mean of the two middle elements (numpy _median -> mean)
                 med[g] = a if (t % 2) else (a + b) / 2.0
-        return np.asarray(totals, dtype=np.int64), med
+        return self._unmap(np.asarray(totals, dtype=np.int64), fsrc), self._unmap(med, fsrc, fill=np.nan)
 
     def _median_windows(self, thr, dirp, hi_bits_full):
         """Per-lag |dz| windows (bit patterns) that very probably hold the lag's median: the
@@ -924,6 +1001,7 @@ class PairEngine:
         idx = np.sort(np.random.default_rng(12345).choice(self.n, size=m, replace=False))
         sub = PairEngine(self._orig_coords[idx], self._orig_values[idx], device=self.device,
                          value_mode=self.vmode)
+        sub.pair_filter = self.pair_filter
         q = self.WINDOW_HALF_QUANTILE
 
         def rank_fn(g, tot):
@@ -943,7 +1021,7 @@ class PairEngine:
         return w_lo, w_hi
 
     # -------------------------------------------------------- materialisation
-    def materialize(self, want=("dist",), edges=None, dirp=None, chunk=1 << 24):
+    def materialize(self, want=("dist",), edges=None, dirp=None, chunk=1 << 24, _raw=False):
         """Condensed arrays (Variogram.distance / pairwise_diffs / lag_groups /
         direction mask) produced on the device in chunks and copied to the host."""
         thr = None if edges is None else sq_threshold_bits(edges)
@@ -990,7 +1068,23 @@ class PairEngine:
                 s_bits, _ = self._amb_keys(amb)
                 g = np.searchsorted(thr, s_bits, side="right")
                 out["groups"][k] = np.where(g >= nl, -1, g)
+        if self.pair_filter is not None and not _raw:
+            out = self._sparse_view(out, want)
         return out
+
+    def _sparse_view(self, out, want):
+        """Sparse (max_dist) spaces: keep the pairs with 0 < d <= max_dist and put them in the
+        order of the reference's triangular CSR matrix (Variogram.py:1210-1227: lower-triangle
+        entries row by row, i.e. pairs (i < j) sorted by j, then i)."""
+        n = self.n
+        if "dist" in out:
+            d = out["dist"]
+        else:
+            d = self.materialize(("dist",), _raw=True)["dist"]
+        keep = np.flatnonzero((d > 0) & (d <= self.max_dist))
+        iu, ju = np.triu_indices(n, 1)
+        order = keep[np.lexsort((iu[keep], ju[keep]))]
+        return {name: out[name][order] for name in want}
 
 
 class KrigeEngine:

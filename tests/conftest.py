@@ -78,3 +78,8 @@ def golden_binners():
 @pytest.fixture(scope="session")
 def golden_estimators():
     return Golden("estimators")
+
+
+@pytest.fixture(scope="session")
+def golden_sparse():
+    return Golden("sparse")
