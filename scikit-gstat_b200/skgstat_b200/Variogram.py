@@ -19,11 +19,13 @@ with numpy's own arithmetic from those scalars (bit-identical edges), and
 device on demand.  The model fit is scipy ``curve_fit`` on n_lags points and
 stays on the CPU, as in the reference (Variogram.py:1584-1821).
 
+Also built on the same kernels: cross / aggregate (2-D ``values``) variograms, the
+histogram-rule binners, the minmax / percentile / entropy estimators, sparse ``max_dist`` spaces.
+
 Out of scope, raising NotImplementedError rather than taking a slow path:
-``samples=`` (ProbabalisticMetricSpace), non-euclidean
-metrics, cross/aggregate (2-D ``values``) variograms, clustering / histogram-rule
-binners, the genton/minmax/percentile/entropy estimators by name, ``fit_method='ml'``
-and harmonised models.
+``samples=`` (ProbabalisticMetricSpace), non-euclidean metrics, the clustering binners
+(kmeans, ward, stable_entropy), the genton estimator by name and harmonised / sum models
+(SURVEY.md section 2 rows 8-15).
 """
 from __future__ import annotations
 
