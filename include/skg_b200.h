@@ -221,6 +221,21 @@ int skg_pair_select_hist(const double* coords, const double* values, int n_value
                          void* scratch, int64_t scratch_bytes,
                          int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
+/* K1a - exact pair counts on a log-spaced grid of the squared distance s:
+ *   cell(s) = clamp((hi32(bits(s)) >> shift) - key0, 0, SKG_CELL_COUNT - 1)
+ * over the (mask-passing) pairs with lo_bits <= bits(s) < hi_bits.  2^(20-shift) cells per octave
+ * of s and no threshold compares: the first sweep of every distance order statistic
+ * (np.median / np.percentile / np.nanpercentile over the distance vector, Variogram.py:1288-1293,
+ * binning.py:70-79, DirectionalVariogram.py:509); the cell holding a wanted rank is narrow enough
+ * to be gathered (skg_pair_select_gather) or refined with nearly every tile culled.
+ *   count [dev, SKG_CELL_COUNT] += pairs per cell;  scratch >= skg_pair_cell_scratch_bytes(n). */
+#define SKG_CELL_COUNT 4096
+int64_t skg_pair_cell_scratch_bytes(int64_t n);
+int skg_pair_cell_counts(const double* coords, int64_t n, int dim, const double* dir,
+                         uint64_t lo_bits, uint64_t hi_bits, int shift, int key0, uint64_t* count,
+                         void* scratch, int64_t scratch_bytes, int64_t tile_begin, int64_t tile_end,
+                         int64_t tile_stride, void* stream);
+
 /* Gather pass: every key whose (segment, bucket) bit is set in `bitmap`
  * ([dev] uint32 words, bit index = g*n_buckets + bucket) is appended to
  * cand_key / cand_slot (slot = g*n_buckets + bucket).  cand_count [dev,1]

@@ -24,6 +24,7 @@ VALUE_SCALAR, VALUE_CROSS, VALUE_AGGREGATE = 0, 1, 2
 VALUE_DIST_S, VALUE_DIST_D, VALUE_DIST_D15 = 3, 4, 5
 VALUE_SQUARE_FLAG = 0x100
 MAX_VALUE_COLUMNS = 8
+CELL_COUNT = 4096
 MODEL_IDS = dict(spherical=0, exponential=1, gaussian=2, cubic=3, stable=4, matern=5)
 KRIGE_OK, KRIGE_LESS_POINTS, KRIGE_SINGULAR = 0, 1, 2
 
@@ -48,6 +49,9 @@ SIGNATURES = {
     "skg_pair_batch_scratch_bytes": (_i64, [_i64, _int]),
     "skg_pair_hist_batch": (_int, [_p, _p, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
                                    _i64, _i64, _i64, _p]),
+    "skg_pair_cell_scratch_bytes": (_i64, [_i64]),
+    "skg_pair_cell_counts": (_int, [_p, _i64, _int, _p, C.c_uint64, C.c_uint64, _int, _int, _p, _p, _i64,
+                                    _i64, _i64, _i64, _p]),
     "skg_pair_select_hist": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
                                     _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_select_gather": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,

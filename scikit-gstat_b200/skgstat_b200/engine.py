@@ -613,53 +613,38 @@ class PairEngine:
             b >>= 1
         return b
 
-    COARSE_CLASSES = 32
-    WINDOWED_SELECT_MIN_PAIRS = 4 * 10 ** 9
-    SELECT_HALF_QUANTILE = 0.025
+    CELL_SHIFT = 11                 # 512 cells per octave of s: a cell spans 0.07 % of d
+    DIRECT_GATHER_LIMIT = 1 << 17   # cells up to this many keys are gathered without a fine histogram
 
-    def _sq_window_classes(self, rank_fn, dirp, limit, hi_bits):
-        """Class boundaries (bit patterns of s) for the counting sweep of a LARGE problem: narrow
-        windows around the quantiles of the wanted ranks, estimated from a random sub-sample of
-        the points (same seed on every rank).  The counting sweep then culls every tile beyond
-        the last window and the fine/gather sweeps see windows of a few percent of the pairs.
-        Purely a speed device: a rank that falls outside its window lands in one of the gap
-        classes and is resolved there, still exactly."""
-        m = int(min(self.n, max(4000, self.n // 4)))
-        if m >= self.n:
-            return None
-        idx = np.sort(np.random.default_rng(54321).choice(self.n, size=m, replace=False))
-        sub = PairEngine(self._orig_coords[idx], device=self.device)
-        sub.pair_filter = self.pair_filter
-        # fractions of the wanted ranks; the totals are proportional up to sampling noise
-        probe = rank_fn(10 ** 9)
-        if not probe or len(probe) > 12:
-            return None
-        fr = sorted(set(min(max(r / 1e9, 0.0), 1.0) for r in probe))
-        q = self.SELECT_HALF_QUANTILE
-
-        def sub_rank_fn(tot):
-            if tot < 2000:
-                return []
-            out = set()
-            for f in fr:
-                out.add(max(0, int((f - q) * tot)))
-                out.add(min(tot - 1, int((f + q) * tot)))
-            return sorted(out)
-
-        vals, tot = sub.sq_order_stats(sub_rank_fn, dirp=dirp, limit=limit)
-        self.launches += sub.launches
-        if not vals:
-            return None
-        spans = []
-        for f in fr:
-            lo = to_bits(vals[max(0, int((f - q) * tot))])
-            hi = to_bits(vals[min(tot - 1, int((f + q) * tot))]) + 1
-            if spans and lo <= spans[-1][1]:      # overlapping windows (e.g. the two median ranks)
-                spans[-1][1] = max(spans[-1][1], hi)
-            else:
-                spans.append([lo, hi])
-        bounds = sorted(set(b for s in spans for b in s if 0 < b < hi_bits))
-        return np.array(bounds + [hi_bits], dtype=np.uint64)
+    def sq_cell_counts(self, dirp, lo_bits: int, hi_bits: int):
+        """Exact counts of the (mask-passing) pairs with lo_bits <= bits(s) < hi_bits on a
+        log-spaced grid of s (skg_pair_cell_counts; shared-memory counters, no threshold
+        compares).  Returns (upper cell boundaries as bit patterns, clipped to [lo, hi]; counts)."""
+        nc, shift = _lib.CELL_COUNT, self.CELL_SHIFT
+        top = ((hi_bits - 1) >> 32) >> shift
+        key0 = int(top) - (nc - 1)
+        cnt = self._buffer("cell_cnt", nc, torch.int64).zero_()
+        need = int(self.lib.skg_pair_cell_scratch_bytes(self.n))
+        scratch = self._buffer("cell_scratch", need, torch.uint8)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_cell_counts(
+                _ptr(self.coords), self.n, self.dim, _hptr(dirp), int(lo_bits), int(hi_bits), shift,
+                key0, _ptr(cnt), _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride,
+                self._stream())
+        _lib.check(rc, "skg_pair_cell_counts")
+        self.launches += 5 if self.t1 > self.t0 else 0
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, _ = self._amb_keys(amb)
+            sb = s_bits[(s_bits >= np.uint64(lo_bits)) & (s_bits < np.uint64(hi_bits))]
+            cell = np.clip(((sb >> np.uint64(32)) >> np.uint64(shift)).astype(np.int64) - key0, 0, nc - 1)
+            cnt += to_device(np.bincount(cell, minlength=nc).astype(np.int64), self.device)
+        D.allreduce_sum_(cnt, self.group)
+        counts = to_host(cnt).astype(np.int64)
+        keys = np.maximum(key0 + 1 + np.arange(nc, dtype=np.int64), 0).astype(np.uint64)
+        thr = np.clip(keys << np.uint64(32 + shift), np.uint64(lo_bits), np.uint64(hi_bits))
+        thr[nc - 1] = hi_bits
+        return thr, counts
 
     def hist_counts(self, thr: np.ndarray, dirp=None) -> np.ndarray:
         """Exact pair counts per class of squared distance for bit-pattern thresholds
@@ -691,10 +676,10 @@ class PairEngine:
         pairs with fl(sqrt(s)) <= limit.  rank_fn(total) -> 0-based ranks.
         Returns (dict rank -> s, total).
 
-        Three sweeps, only the last two touch atomics and only for ~1/32 of the pairs per
-        wanted rank: (1) exact counts over COARSE_CLASSES classes linear in s with the
-        fused-pass kernel (private counters); (2) fine bucket histogram restricted to the
-        classes that hold a wanted rank; (3) gather of the target buckets."""
+        Sweep 1: exact counts on a log-spaced grid of 4096 cells (sq_cell_counts).  A cell that
+        holds a wanted rank spans 0.07 % of d: with few keys it is gathered directly (sweep 2);
+        otherwise a fine bucket histogram and a gather run inside it (sweeps 2 and 3), where
+        nearly every tile is culled.  Ties (crowded single values) refine further, exactly."""
         from ._exact import sq_upper_inclusive_bits
         ub = self.sq_upper_bound()
         hi_bits = to_bits(ub) + 1
@@ -704,48 +689,18 @@ class PairEngine:
         if self.pair_filter is not None:          # sparse space: 0 < d <= max_dist only
             hi_bits = min(hi_bits, self.pair_filter[0])
             zero_lo = 1 if self.pair_filter[1] else 0
-        hi_val = from_bits(hi_bits)
-
-        def default_classes():
-            C = self.COARSE_CLASSES
-            edges_s = [hi_val * (k + 1) / C for k in range(C - 1)] + [hi_val]
-            t = np.maximum.accumulate(np.array([to_bits(x) for x in edges_s], dtype=np.uint64))
-            t[-1] = hi_bits
-            return t
-
-        # without mask, limit or NaN coordinates the number of keys is known: the counting
-        # sweep can then stop at the last window and cull everything beyond it
-        known_total = None
-        if dirp is None and limit is None and self.pair_filter is None:
-            if self._all_finite is None:
-                self._all_finite = bool(np.isfinite(self._orig_coords).all())
-            if self._all_finite:
-                known_total = self.n_pairs
-        thr = None
-        if self.n_pairs >= self.WINDOWED_SELECT_MIN_PAIRS:
-            thr = self._sq_window_classes(rank_fn, dirp, limit, hi_bits)
-            if thr is not None and known_total is not None and thr.size > 1:
-                thr = thr[:-1]  # drop the tail class [last window, upper bound)
-        windowed = thr is not None
-        if thr is None:
-            thr = default_classes()
-        while True:
-            counts = self.hist_counts(thr, dirp)
-            total = known_total if (windowed and known_total is not None) else int(counts.sum())
-            ranks = sorted(set(int(r) for r in rank_fn(total)))
-            for r in ranks:
-                if not (0 <= r < total):
-                    raise ValueError("rank %d outside [0, %d)" % (r, total))
-            if not ranks:
-                return {}, total
-            cum = np.cumsum(counts)
-            cls = np.searchsorted(cum, np.asarray(ranks, dtype=np.int64), side="right")
-            if windowed and (cls >= thr.size).any():
-                thr, windowed = default_classes(), False  # a rank lies beyond the sampled windows
-                continue
-            break
+        thr, counts = self.sq_cell_counts(dirp, zero_lo, hi_bits)
+        total = int(counts.sum())
+        ranks = sorted(set(int(r) for r in rank_fn(total)))
+        for r in ranks:
+            if not (0 <= r < total):
+                raise ValueError("rank %d outside [0, %d)" % (r, total))
+        if not ranks:
+            return {}, total
+        cum = np.cumsum(counts)
+        cls = np.searchsorted(cum, np.asarray(ranks, dtype=np.int64), side="right")
         wanted = sorted(set(int(c) for c in cls))
-        # window table: [lo_1, hi_1, lo_2, hi_2, ...]; class 2w+1 = inside window w
+        # window table: [lo_1, hi_1, lo_2, hi_2, ...]; segment 2w+1 = inside window w
         bounds, win_lo, win_hi, base = [], [], [], []
         for c in wanted:
             lo = int(thr[c - 1]) if c > 0 else zero_lo
@@ -765,12 +720,23 @@ class PairEngine:
         seg_ranks = {}
         for r, c in zip(ranks, cls):
             seg_ranks.setdefault(seg_of_class[int(c)], []).append(r - base[wanted.index(int(c))])
-        nb = 1 << 10
-        while nb < (1 << 16) and nb * 256 < int(counts[wanted].max()):
-            nb <<= 1
-        while nseg * nb > (1 << 22) and nb > 256:
-            nb >>= 1
-        rh, rg = self._select_runner(_lib.KEY_SQDIST, wthr, dirp, nb)
+        biggest = int(counts[wanted].max())
+        if biggest <= self.DIRECT_GATHER_LIMIT and int(counts[wanted].sum()) <= (1 << 22):
+            # the wanted cells are small: one bucket per cell, counts already known -> no
+            # histogram sweep, straight to the gather
+            nb = 1
+            known = np.zeros((nseg, 1), dtype=np.int64)
+            for w, c in enumerate(wanted):
+                known[2 * w + 1, 0] = counts[c]
+            _, rg = self._select_runner(_lib.KEY_SQDIST, wthr, dirp, nb)
+            rh = lambda lo, hi, sc: known
+        else:
+            nb = 1 << 10
+            while nb < (1 << 16) and nb * 256 < biggest:
+                nb <<= 1
+            while nseg * nb > (1 << 22) and nb > 256:
+                nb >>= 1
+            rh, rg = self._select_runner(_lib.KEY_SQDIST, wthr, dirp, nb)
         vals, totals = exact_select(nseg, lo_bits, hi_bits_l, nb,
                                     lambda g, t: seg_ranks.get(g, []), rh, rg)
         out = {}
@@ -778,7 +744,7 @@ class PairEngine:
             w = wanted.index(int(c))
             seg = 2 * w + 1
             if totals[seg] != int(counts[int(c)]):
-                raise RuntimeError("coarse/fine count mismatch in class %d" % int(c))
+                raise RuntimeError("cell / window count mismatch in cell %d" % int(c))
             out[r] = vals[seg][r - base[w]]
         return out, total
 

@@ -123,7 +123,8 @@ def exact_select(nseg: int, lo_bits: Sequence[int], hi_bits: Sequence[int], n_bu
                 z = np.searchsorted(slots, slot, side="right")
                 if z - a != cnt:
                     raise RuntimeError("bucket (%d,%d): gathered %d, counted %d" % (g, b, z - a, cnt))
-                vals = np.sort(keys[a:z])
+                idx = sorted(set(int(r - base) for r in rs))
+                vals = np.partition(keys[a:z], idx)   # exact order statistics, O(n)
                 for r in rs:
                     values[g][r] = float(vals[r - base])
     return values, totals

@@ -212,10 +212,11 @@ def test_full_size_properties(skg):
 
 
 def test_windowed_select_paths_are_exact(skg, monkeypatch):
-    """The large-problem paths (sample-derived windows for the distance order statistics and
-    for Dowd's per-lag medians) forced on at a size the dense oracle can check."""
+    """The large-problem paths (fine histogram + gather inside a crowded distance cell instead of
+    the direct gather; sample-derived windows for Dowd's per-lag medians) forced on at a size the
+    dense oracle can check."""
     from skgstat_b200.engine import PairEngine
-    monkeypatch.setattr(PairEngine, "WINDOWED_SELECT_MIN_PAIRS", 0)
+    monkeypatch.setattr(PairEngine, "DIRECT_GATHER_LIMIT", 0)
     monkeypatch.setattr(PairEngine, "WINDOWED_MEDIAN_MIN_PAIRS", 0)
     c = random_points(9000, 1000.0, 2, seed=17)
     v = gaussian_field(c, 80.0, seed=17)

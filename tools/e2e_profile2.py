@@ -12,4 +12,4 @@ for _ in range(3): skg.Variogram(c, v, **kw).experimental
 pr = cProfile.Profile(); pr.enable()
 for _ in range(10): skg.Variogram(c.copy(), v.copy(), **kw).experimental
 pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
