@@ -781,9 +781,9 @@ class PairEngine:
     WINDOWED_MEDIAN_MIN_PAIRS = 2 * 10 ** 8   # below this the plain two-sweep select is fast enough
     WINDOW_HALF_QUANTILE = 0.04
 
-    def _dz_select(self, thr, dirp, lo_bits, hi_bits, rank_fn):
+    def _dz_select(self, thr, dirp, lo_bits, hi_bits, rank_fn, n_keys=None):
         nl = int(thr.size)
-        nb = self._buckets_for(self.n_pairs, nl)
+        nb = self._buckets_for(self.n_pairs if n_keys is None else n_keys, nl)
         rh, rg = self._select_runner(_lib.KEY_ABSDZ, thr, dirp, nb)
         return exact_select(nl, lo_bits, hi_bits, nb, rank_fn, rh, rg)
 
@@ -924,8 +924,11 @@ class PairEngine:
                         return []                     # window missed the median: handled below
                     return [int(ra[g]), int(rb[g])]
 
+                # the windows hold ~2 * WINDOW_HALF_QUANTILE of the in-range pairs: size the bucket
+                # histogram (device memory, D2H copy, host prefix sums) for that population
                 vals, wtot = self._dz_select(thr, dirp, [int(x) for x in w_lo],
-                                             [int(x) for x in w_hi], rel_rank_fn)
+                                             [int(x) for x in w_hi], rel_rank_fn,
+                                             n_keys=int(counts.sum() * 2.5 * self.WINDOW_HALF_QUANTILE) + 1)
                 totals = [int(c) for c in counts]
                 med_lo = [None] * nl
                 med_hi = [None] * nl
