@@ -1,0 +1,115 @@
+"""Seeded differential test: random small configurations (sizes, dimensions, duplicates, ties,
+lag counts, maxlag forms, estimators, binners) through the drop-in classes against the dense
+oracle.  Catches interactions the structured cases miss."""
+import warnings
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from oracle import variogram as ov
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def skg():
+    import skgstat_b200
+    skgstat_b200._lib.load()
+    return skgstat_b200
+
+
+def _config(rng):
+    n = int(rng.choice([2, 3, 5, 17, 64, 65, 130, 255, 256, 257, 300, 511, 513, 700]))
+    dim = int(rng.choice([1, 2, 2, 2, 3]))
+    kind = rng.choice(["uniform", "lattice", "clustered", "dup"])
+    if kind == "lattice":
+        c = rng.integers(0, 12, size=(n, dim)).astype(float)
+    elif kind == "clustered":
+        c = rng.normal(0, 1, size=(n, dim)) + rng.integers(0, 3, size=(n, 1)) * 10.0
+    else:
+        c = rng.random((n, dim)) * float(rng.choice([1.0, 100.0, 1e4]))
+        if kind == "dup" and n > 4:
+            c[rng.integers(0, n, size=n // 4)] = c[0]
+    v = rng.normal(size=n) * float(rng.choice([1.0, 50.0])) + float(rng.choice([0.0, 1e3]))
+    if rng.random() < 0.2:
+        v = np.round(v, 0)
+    est = str(rng.choice(["matheron", "cressie", "dowd"]))
+    bf = str(rng.choice(["even", "even", "uniform"]))
+    n_lags = int(rng.choice([1, 2, 5, 10, 25, 40]))
+    ml = rng.choice(["none", "median", "mean", "frac", "abs"])
+    return c if dim > 1 else c[:, 0], v, est, bf, n_lags, str(ml)
+
+
+def test_random_configurations_match_the_oracle(skg):
+    rng = np.random.default_rng(20240607)
+    done = 0
+    for it in range(140):
+        c, v, est, bf, n_lags, mlk = _config(rng)
+        d = ov.distance(c)
+        if not (np.nanmax(d) > 0):
+            continue
+        ml = {"none": None, "median": "median", "mean": "mean", "frac": 0.37,
+              "abs": float(np.round(0.6 * d.max(), 6)) + 1.0}[mlk]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                ref = ov.dense_variogram(c, v, est, bf, n_lags, ml)
+            except Exception:
+                continue    # the reference itself cannot form these bins (e.g. empty percentile input)
+            edges = np.asarray(ref["bins"], dtype=float)
+            if np.any(np.diff(edges) < 0) or not np.all(np.isfinite(edges)):
+                continue
+            V = skg.Variogram(c, v, estimator=est, bin_func=bf, n_lags=n_lags, maxlag=ml, fit_method=None)
+            msg = "iteration %d: n=%d est=%s bf=%s n_lags=%d maxlag=%r" % (it, len(v), est, bf, n_lags, ml)
+            assert_array_equal(V.bins, ref["bins"], err_msg=msg)
+            assert_array_equal(V.bin_count, ref["bin_count"], err_msg=msg)
+            assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, atol=1e-300, equal_nan=True,
+                            err_msg=msg)
+        done += 1
+    assert done >= 100
+
+
+def test_random_kriging_configurations_match_the_oracle(skg):
+    """Random sample sets / targets / neighbourhood sizes through OrdinaryKriging against the
+    oracle restatement of Kriging.py:405-650 (well-conditioned models only, rtol 1e-9)."""
+    from oracle import kriging as okr
+    rng = np.random.default_rng(777)
+    done = 0
+    for it in range(40):
+        n = int(rng.choice([6, 20, 64, 65, 200, 500]))
+        dim = int(rng.choice([2, 2, 3]))
+        c = rng.random((n, dim)) * 100.0
+        if rng.random() < 0.3 and n > 10:
+            c[rng.integers(0, n, size=3)] = c[1]            # duplicated coordinates are removed
+        v = np.sin(c[:, 0] / 15.0) + 0.1 * rng.normal(size=n)
+        model = str(rng.choice(["spherical", "exponential", "cubic", "stable", "matern"]))
+        rng_r = float(rng.choice([15.0, 40.0, 90.0]))
+        sill = float(rng.choice([0.5, 2.0]))
+        nug = float(rng.choice([0.0, 0.0, 0.05]))
+        shape = {"stable": 1.2, "matern": 0.8}.get(model)
+        minp = int(rng.choice([1, 3, 5]))
+        maxp = int(rng.choice([5, 8, 16, 33, 64]))
+        if minp > maxp:
+            minp = maxp
+        m = 60
+        t = rng.random((m, dim)) * 120.0 - 10.0
+        t[:5] = c[:5]                                       # targets on top of samples
+        desc = dict(model=model, effective_range=rng_r, sill=sill, nugget=nug, dist_func="euclidean")
+        if model == "stable":
+            desc["shape"] = shape
+        if model == "matern":
+            desc["smoothness"] = shape
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ok = skg.OrdinaryKriging(desc, min_points=minp, max_points=maxp, coordinates=c, values=v)
+            z = ok.transform(*[t[:, k] for k in range(dim)])
+            zr, sr, st = okr.krige(c, v, t, model, rng_r, sill, nug, shape, minp, maxp)
+        msg = "iteration %d: n=%d dim=%d model=%s range=%g maxp=%d" % (it, n, dim, model, rng_r, maxp)
+        good = st == 0
+        assert_array_equal(np.isnan(z), ~good | np.isnan(zr), err_msg=msg)
+        fin = good & np.isfinite(zr)
+        assert_allclose(z[fin], zr[fin], rtol=1e-8, atol=1e-9, err_msg=msg)
+        assert_allclose(ok.sigma[fin], sr[fin], rtol=1e-7, atol=1e-8 * sill, err_msg=msg)
+        done += 1
+    assert done == 40
