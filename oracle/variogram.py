@@ -195,9 +195,13 @@ def compass_mask(angles, dists, azimuth, tolerance, bandwidth=None):
 
 
 def resolve_bandwidth(d, bandwidth):
-    """DirectionalVariogram.py:503-520 ('q33' -> np.percentile(d, 33))."""
+    """DirectionalVariogram.py:497-516 ('q33' -> np.percentile(d, 33)).  A width beyond the largest
+    distance is NOT stored (:513-515 only print a note), so the property falls back to 0 (:498-499)
+    and the triangle's strip collapses onto the azimuth axis - restated as is."""
     if isinstance(bandwidth, str):
         return np.percentile(d, int(bandwidth[1:]))
+    if bandwidth > np.max(d):
+        return 0
     return bandwidth
 
 

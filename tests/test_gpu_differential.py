@@ -113,3 +113,52 @@ def test_random_kriging_configurations_match_the_oracle(skg):
         assert_allclose(ok.sigma[fin], sr[fin], rtol=1e-7, atol=1e-8 * sill, err_msg=msg)
         done += 1
     assert done == 40
+
+
+def test_random_directional_configurations_match_the_oracle(skg):
+    """Random azimuths / tolerances / bandwidths (incl. the extremes) on random and lattice
+    points: exercises the guard-band resolution and the direction culling of tiles and warps."""
+    rng = np.random.default_rng(4242)
+    done = 0
+    for it in range(60):
+        n = int(rng.choice([40, 257, 600, 1100, 2300]))
+        if rng.random() < 0.3:
+            c = rng.integers(0, 25, size=(n, 2)).astype(float)
+        else:
+            c = rng.random((n, 2)) * float(rng.choice([10.0, 1000.0]))
+        v = rng.normal(size=n)
+        az = float(rng.choice([0, 45, 90, 135, 180, -120, 30.5, -179.9, -45]))
+        tol = float(rng.choice([1.0, 10.0, 22.5, 45.0, 90.0, 170.0, 180.0]))
+        model = str(rng.choice(["triangle", "compass"]))
+        span = float(c.max() - c.min())
+        bw = rng.choice(["q33", "q10", "abs_small", "abs_large"])
+        bw = {"q33": "q33", "q10": "q10", "abs_small": 0.02 * span, "abs_large": 2.0 * span}[str(bw)]
+        est = str(rng.choice(["matheron", "cressie", "dowd"]))
+        bf = str(rng.choice(["even", "uniform"]))
+        n_lags = int(rng.choice([4, 10, 20]))
+        ml = rng.choice(["none", "median", "frac"])
+        ml = {"none": None, "median": "median", "frac": 0.5}[str(ml)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                ref = ov.dense_directional(c, v, est, bf, n_lags, ml, az, tol, bw, model)
+            except Exception:
+                continue
+            edges = np.asarray(ref["bins"], dtype=float)
+            if ref["mask_count"] == 0 or np.any(np.diff(edges) < 0) or not np.all(np.isfinite(edges)):
+                continue
+            msg = ("iteration %d: n=%d az=%g tol=%g bw=%r model=%s est=%s bf=%s n_lags=%d maxlag=%r"
+                   % (it, n, az, tol, bw, model, est, bf, n_lags, ml))
+            try:
+                V = skg.DirectionalVariogram(c, v, estimator=est, bin_func=bf, n_lags=n_lags, maxlag=ml,
+                                             azimuth=az, tolerance=tol, bandwidth=bw,
+                                             directional_model=model, fit_method=None)
+                bins = V.bins
+            except Exception as e:
+                raise AssertionError(msg + " -> " + repr(e) + " (oracle mask_count=%d)" % ref["mask_count"])
+            assert_array_equal(bins, ref["bins"], err_msg=msg)
+            assert_array_equal(V.bin_count, ref["bin_count"], err_msg=msg)
+            assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, atol=1e-300, equal_nan=True,
+                            err_msg=msg)
+        done += 1
+    assert done >= 40
