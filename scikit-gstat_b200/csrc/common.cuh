@@ -61,16 +61,6 @@ int build_dir_params(const double* dir, int dim, DirParams* out);
 
 // ---------------------------------------------------------------- device ---
 
-__device__ __forceinline__ int find_bin(uint64_t sb, const uint64_t* __restrict__ sThr,
-                                        const uint8_t* __restrict__ sLut, int key0, int shift,
-                                        int ncell, int emax) {
-  int c = (int)((uint32_t)(sb >> 32) >> shift) - key0;
-  c = min(max(c, 0), ncell - 1);
-  int g = sLut[c];
-  for (int e = 0; e < emax; ++e) g += (sb >= sThr[g]) ? 1 : 0;
-  return g;
-}
-
 // DirectionalVariogram.py:348-413 + :659-714 / :749-782.
 // Fast path: acute angle test through dot/cross products against the azimuth
 // direction; pairs within a relative 2^-40 guard band of either decision

@@ -1,16 +1,17 @@
-// Pair-sweep kernels (K1-K4 of SURVEY.md section 2.2) for sm_100a.
+// Host side of the pair sweeps (K1-K4 of SURVEY.md section 2.2) for sm_100a: culling prelude
+// kernels, the fused-pass instantiations for scalar values, guard-band pair collection,
+// materialisation and the C ABI.  The sweep kernels themselves live in pair_sweep.cuh; the
+// other instantiations in pair_select.cu (select passes, cell counts), pair_mv.cu (multi-column
+// values) and pair_batch.cu (many value vectors per sweep).
 //
-// All kernels walk the upper triangle of the N x N pair matrix in
-// TILE x TILE point tiles.  A CTA of BLOCK threads keeps RI = TILE/BLOCK
-// "i" points per thread in registers, stages the "j" tile in shared memory with
-// coalesced loads and reads it back as warp-wide broadcasts.  The N(N-1)/2
-// distance vector the reference materialises (MetricSpace.py:151-153,
-// Variogram.py:1202-1208) never exists.
+// All kernels walk the upper triangle of the N x N pair matrix in TILE x TILE point tiles.
+// Threads keep their "i" points in registers, the "j" tile (or chunk) sits in shared memory and
+// is read back as warp-wide broadcasts.  The N(N-1)/2 distance vector the reference
+// materialises (MetricSpace.py:151-153, Variogram.py:1202-1208) never exists.
 //
-// Per pair:  s = fl(fl(dx*dx) + fl(dy*dy)) [+ fl(dw*dw)]  - scipy's euclidean
-// operand order, no FMA (explicit __dmul_rn/__dadd_rn), so that every
-// comparison against the squared-space thresholds reproduces np.digitize on
-// d = sqrt(s) exactly (see include/skg_b200.h).
+// Per pair:  s = fl(fl(dx*dx) + fl(dy*dy)) [+ fl(dw*dw)]  - scipy's euclidean operand order, no
+// FMA (explicit __dmul_rn/__dadd_rn), so that every comparison against the squared-space
+// thresholds reproduces np.digitize on d = sqrt(s) exactly (see include/skg_b200.h).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -103,10 +104,6 @@ __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
   }
 }
 
-__device__ __forceinline__ void load_tables(const BinTable& tab, uint64_t* sThr, uint8_t* sLut) {
-  for (int k = threadIdx.x; k < THR_MAX; k += blockDim.x) sThr[k] = tab.thr[k];
-  for (int k = threadIdx.x; k < tab.ncell; k += blockDim.x) sLut[k] = tab.lut[k];
-}
 
 
 template <int DIM>
