@@ -238,8 +238,8 @@ class Variogram:
             raise NotImplementedError("n_lags string values not implemented")
         if isinstance(n, bool) or not isinstance(n, (int, np.integer)) or n < 1:
             raise ValueError("n_lags has to be a positive integer")
-        if n > _lib.MAX_LAGS:
-            raise ValueError("n_lags > %d is not supported by the GPU lag table" % _lib.MAX_LAGS)
+        if n > 100000:
+            raise ValueError("n_lags > 100000 is not supported")
         self._n_lags = int(n)
         self._n_lags_passed_value = n
         self._bins = None
@@ -429,9 +429,9 @@ class Variogram:
                 m3 = s3 / n - 3.0 * mean * (s2 / n) + 2.0 * mean ** 3
                 stats["g1"] = m3 / stats["std"] ** 3 if stats["std"] > 0 else 0.0
         edges = binning.auto_edges(method, total, d[0], d[total - 1], **stats)
-        if limit_check and len(edges) > _lib.MAX_LAGS:
-            raise ValueError("bin_func=%r derives %d lag classes; the GPU lag table holds %d"
-                             % (method, len(edges), _lib.MAX_LAGS))
+        if limit_check and len(edges) > 100000:
+            raise ValueError("bin_func=%r derives %d lag classes; at most 100000 are supported"
+                             % (method, len(edges)))
         return edges, len(edges)
 
     @property
@@ -480,6 +480,8 @@ class Variogram:
         else:
             raise ValueError("The estimator has to be a string or callable.")
 
+    LAG_CHUNK = 240   # lag classes per sweep (the kernels' lag table holds SKG_MAX_LAGS = 250)
+
     def _calc_experimental(self):
         if self._exp is not None:
             return
@@ -489,6 +491,31 @@ class Variogram:
             raise ValueError("bins must be monotonically increasing")
         eng = self._engine()
         dirp = self._dirp()
+        if self._estimator_name is None:
+            # user callable on materialised lag classes (reference operator contract)
+            classes = list(self.lag_classes())
+            cnt = np.fromiter((c.size for c in classes), dtype=np.int64)
+            exp = np.fromiter(map(self._estimator, classes), dtype=float)
+        elif len(edges) <= self.LAG_CHUNK:
+            cnt, exp = self._experimental_of(eng, edges, thr, dirp)
+        else:
+            # more lag classes than one sweep holds: sweeps over consecutive groups of classes, each
+            # with the previous edge as a leading class whose result is dropped (tiles beyond a
+            # group's last edge are culled, so k groups cost about k/2 full sweeps)
+            cnts, exps = [], []
+            step = self.LAG_CHUNK - 1
+            for a in range(0, len(edges), step):
+                z = min(len(edges), a + step)
+                lead = 1 if a else 0
+                c, e = self._experimental_of(eng, edges[a - lead:z], thr[a - lead:z], dirp)
+                cnts.append(c[lead:])
+                exps.append(e[lead:])
+            cnt, exp = np.concatenate(cnts), np.concatenate(exps)
+        self._bin_count = np.asarray(cnt, dtype=np.int64)
+        self._exp = np.asarray(exp, dtype=float)
+
+    def _experimental_of(self, eng, edges, thr, dirp):
+        """(pair counts, semi-variances) of the lag classes with the given upper edges."""
         name = self._estimator_name
         if name == "matheron":
             cnt, ssq, _ = eng.hist(edges, _lib.STAT_SUM_SQ, dirp, thr_bits=thr)
@@ -513,17 +540,12 @@ class Variogram:
             cnt = np.asarray(tot, dtype=np.int64)
             exp = np.array([binning.percentile_from_order_stats(tot[g], p, lambda r, g=g: vals[g][r])
                             if tot[g] else np.nan for g in range(len(edges))])
-        elif name == "entropy":  # Variogram.py:2065-2075 + util/shannon.py:27-34
+        else:  # "entropy": Variogram.py:2065-2075 + util/shannon.py:27-34
             value_edges = self._entropy_value_edges()
             hist = eng.dz_value_histogram(edges, value_edges, dirp, thr_bits=thr)
             cnt = eng.hist_counts(thr, dirp)
             exp = np.array([estimators.shannon_from_counts(hist[g]) for g in range(len(edges))])
-        else:  # user callable on materialised lag classes (reference operator contract)
-            classes = list(self.lag_classes())
-            cnt = np.fromiter((c.size for c in classes), dtype=np.int64)
-            exp = np.fromiter(map(self._estimator, classes), dtype=float)
-        self._bin_count = np.asarray(cnt, dtype=np.int64)
-        self._exp = np.asarray(exp, dtype=float)
+        return np.asarray(cnt, dtype=np.int64), np.asarray(exp, dtype=float)
 
     def experimental_batch(self, values):
         """Experimental variograms of K value vectors observed at THIS instance's coordinates,
@@ -540,7 +562,8 @@ class Variogram:
         thr = sq_threshold_bits(edges)
         eng = self._X.engine(self._process_group)
         name = self._estimator_name
-        if name in ("matheron", "cressie") and len(edges) <= eng.lib.skg_pair_batch_max_lags():
+        if name in ("matheron", "cressie") and len(edges) <= min(eng.lib.skg_pair_batch_max_lags(),
+                                                                  self.LAG_CHUNK - 2):
             stat = _lib.STAT_SUM_SQ if name == "matheron" else _lib.STAT_SUM_SQRT
             cnt, sums = eng.hist_batch(edges, V, stat, self._dirp(), thr_bits=thr)
             fin = estimators.finalize_matheron if name == "matheron" else estimators.finalize_cressie
@@ -632,6 +655,13 @@ class Variogram:
 
     def lag_groups(self):
         """Lag class of every pair, -1 outside (Variogram.py:1989-2006)."""
+        if self._groups is None and len(self.bins) > self.LAG_CHUNK:
+            # materialising accessor beyond the kernels' lag table: digitize the materialised vector
+            g = np.digitize(self.distance, self.bins)
+            g = np.where(g == len(self.bins), -1, g)
+            if self._dirp() is not None:
+                g[~self._direction_mask()] = -1
+            self._groups = g
         if self._groups is None:
             out = self._engine().materialize(("groups",), edges=self.bins, dirp=self._dirp())
             self._groups = out["groups"]

@@ -62,8 +62,25 @@ def test_auto_binner_limits_and_setters(skg):
     assert n_sturges == len(V.bins) == int(np.ceil(np.log2(3000 * 2999 // 2) + 1))
     V.bin_func = "doane"
     assert len(V.bins) >= n_sturges and V.n_lags == len(V.bins)
-    with pytest.raises(ValueError, match="lag classes"):
-        skg.Variogram(c, v, bin_func="sqrt", fit_method=None).bins     # 2121 classes
+    # 2121 lag classes: more than one sweep's lag table holds -> consecutive groups of classes
+    from oracle import variogram as ov
+    big = skg.Variogram(c, v, bin_func="sqrt", fit_method=None)
+    d = ov.distance(c)
+    ref_edges = np.histogram_bin_edges(d, bins="sqrt")[1:]
+    assert_array_equal(big.bins, ref_edges)
+    assert big.n_lags == len(ref_edges) == 2121
+    g = ov.lag_groups(d, ref_edges)
+    assert_array_equal(big.bin_count, np.bincount(g[g >= 0], minlength=len(ref_edges)))
+    dz = ov.pairwise_diffs(v)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref_exp = np.bincount(g[g >= 0], weights=dz[g >= 0] ** 2, minlength=len(ref_edges)) / (2.0 * big.bin_count)
+    assert_allclose(big.experimental, ref_exp, rtol=1e-12, equal_nan=True)
+    for est in ("cressie", "dowd"):
+        many = skg.Variogram(c[:1200], v[:1200], estimator=est, n_lags=600, maxlag="median", fit_method=None)
+        ref = ov.dense_variogram(c[:1200], v[:1200], est, "even", 600, "median")
+        assert_array_equal(many.bin_count, ref["bin_count"])
+        assert_allclose(many.experimental, ref["experimental"], rtol=1e-12, equal_nan=True)
+    assert_array_equal(many.lag_groups(), ov.lag_groups(ov.distance(c[:1200]), ref["bins"]))
     with pytest.raises(NotImplementedError):
         skg.Variogram(c, v, bin_func="kmeans", fit_method=None)
     with pytest.raises(ValueError):
