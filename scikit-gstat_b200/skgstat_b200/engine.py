@@ -572,7 +572,10 @@ class PairEngine:
                 collect_max.append(int(mx.item()))
             return to_host(hist)
 
-        def run_gather(lo, hi, sc, bitmap, cap):
+        def run_gather(lo, hi, sc, bitmap, cap, want=None):
+            """want = [(slot, [ranks relative to the slot's keys])]: the order statistics are
+            picked on the device (sort of the gathered keys, one small copy back) and
+            {slot: (count, {rank: key})} is returned instead of the raw candidates."""
             cap = int(cap)
             keys = self._buffer("gather_keys", max(cap, 1), torch.float64)
             slots = self._buffer("gather_slots", max(cap, 1), torch.int32)
@@ -601,8 +604,28 @@ class PairEngine:
                                                      self.device)])
             k = D.allgather_varlen(keys, self.group)
             s = D.allgather_varlen(slots, self.group)
-            return to_host(k), to_host(s).view(np.uint32).astype(np.int64)
+            if want is None:
+                return to_host(k), to_host(s).view(np.uint32).astype(np.int64)
+            picks, layout = [], []
+            for slot, rel in want:
+                sl32 = int(np.array([slot], dtype=np.uint32).view(np.int32)[0])
+                srt = torch.sort(k[s == sl32]).values
+                idx = torch.tensor([min(r, max(srt.numel() - 1, 0)) for r in rel], dtype=torch.int64,
+                                   device=self.device)
+                vals = srt[idx] if srt.numel() else torch.zeros(len(rel), dtype=torch.float64,
+                                                                device=self.device)
+                picks.append(torch.cat([torch.tensor([float(srt.numel())], dtype=torch.float64,
+                                                     device=self.device), vals]))
+                layout.append((slot, list(rel)))
+            flat = to_host(torch.cat(picks)) if picks else np.zeros(0)
+            out, pos = {}, 0
+            for slot, rel in layout:
+                cnt_slot = int(flat[pos])
+                out[slot] = (cnt_slot, {r: float(flat[pos + 1 + i]) for i, r in enumerate(rel)})
+                pos += 1 + len(rel)
+            return out
 
+        run_gather.device_pick = True
         return run_hist, run_gather
 
     def _buckets_for(self, n_keys, nseg):

@@ -110,6 +110,18 @@ def exact_select(nseg: int, lo_bits: Sequence[int], hi_bits: Sequence[int], n_bu
             for g, b, _, _, _ in batch:
                 slot = g * n_buckets + b
                 bitmap[slot >> 5] |= np.uint32(1 << (slot & 31))
+            if getattr(run_gather, "device_pick", False):
+                # the runner sorts the gathered keys where they are and returns only the wanted ranks
+                want = [(g * n_buckets + b, sorted(set(int(r - base) for r in rs)))
+                        for g, b, base, cnt, rs in batch]
+                picked = run_gather(lo, hi, sc, bitmap, cap, want)
+                for g, b, base, cnt, rs in batch:
+                    got, vals = picked[g * n_buckets + b]
+                    if got != cnt:
+                        raise RuntimeError("bucket (%d,%d): gathered %d, counted %d" % (g, b, got, cnt))
+                    for r in rs:
+                        values[g][r] = vals[int(r - base)]
+                continue
             keys, slots = run_gather(lo, hi, sc, bitmap, cap)
             keys = np.asarray(keys, dtype=np.float64)
             slots = np.asarray(slots, dtype=np.int64)
