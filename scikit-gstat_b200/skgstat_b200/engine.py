@@ -637,7 +637,7 @@ class PairEngine:
         return b
 
     CELL_SHIFT = 11                 # 512 cells per octave of s: a cell spans 0.07 % of d
-    DIRECT_GATHER_LIMIT = 1 << 17   # cells up to this many keys are gathered without a fine histogram
+    DIRECT_GATHER_LIMIT = 1 << 22   # cells up to this many keys are gathered (and sorted on the device) without a fine histogram
 
     def sq_cell_counts(self, dirp, lo_bits: int, hi_bits: int):
         """Exact counts of the (mask-passing) pairs with lo_bits <= bits(s) < hi_bits on a
@@ -744,7 +744,8 @@ class PairEngine:
         for r, c in zip(ranks, cls):
             seg_ranks.setdefault(seg_of_class[int(c)], []).append(r - base[wanted.index(int(c))])
         biggest = int(counts[wanted].max())
-        if biggest <= self.DIRECT_GATHER_LIMIT and int(counts[wanted].sum()) <= (1 << 22):
+        direct = biggest <= self.DIRECT_GATHER_LIMIT and int(counts[wanted].sum()) <= (1 << 23)
+        if direct:
             # the wanted cells are small: one bucket per cell, counts already known -> no
             # histogram sweep, straight to the gather
             nb = 1
@@ -752,7 +753,13 @@ class PairEngine:
             for w, c in enumerate(wanted):
                 known[2 * w + 1, 0] = counts[c]
             _, rg = self._select_runner(_lib.KEY_SQDIST, wthr, dirp, nb)
-            rh = lambda lo, hi, sc: known
+            calls = []
+
+            def rh(lo, hi, sc):
+                if calls:   # a second histogram request would mean a refinement the known counts cannot serve
+                    raise RuntimeError("direct gather asked for a refinement")
+                calls.append(1)
+                return known
         else:
             nb = 1 << 10
             while nb < (1 << 16) and nb * 256 < biggest:
@@ -760,8 +767,12 @@ class PairEngine:
             while nseg * nb > (1 << 22) and nb > 256:
                 nb >>= 1
             rh, rg = self._select_runner(_lib.KEY_SQDIST, wthr, dirp, nb)
+        # direct mode: one bucket per cell whatever its size (never refine by count; a cell that is a
+        # single bit pattern is still answered without a gather)
         vals, totals = exact_select(nseg, lo_bits, hi_bits_l, nb,
-                                    lambda g, t: seg_ranks.get(g, []), rh, rg)
+                                    lambda g, t: seg_ranks.get(g, []), rh, rg,
+                                    gather_limit=1 << 24,
+                                    bucket_limit=(1 << 62) if direct else (1 << 22))
         out = {}
         for r, c in zip(ranks, cls):
             w = wanted.index(int(c))
