@@ -91,3 +91,45 @@ def test_thresholds_reproduce_digitize():
     T = np.array([sq_threshold(e) for e in edges])
     assert (np.digitize(d, edges) == np.searchsorted(T, s, side="right")).all()
     assert from_bits(to_bits(3.25)) == 3.25
+
+
+def test_single_bucket_with_known_counts_needs_no_histogram_pass():
+    """Direct mode of engine.sq_order_stats: one bucket per window, counts known from the cell
+    sweep.  The histogram callback is answered from those counts; with the bucket limit lifted
+    the select goes straight to the gather (and never loops on a refinement it cannot serve),
+    also through the device-pick protocol of the gather callback."""
+    rng = np.random.default_rng(5)
+    keys = np.sort(rng.random(6000) * 3.0 + 1.0)
+    lo_b, hi_b = to_bits(1.5), to_bits(2.5)
+    inside = keys[(keys.view(np.uint64) >= lo_b) & (keys.view(np.uint64) < hi_b)]
+    _, rg = emulate([keys], 1)
+    calls = []
+
+    def rh(lo, hi, sc):
+        assert not calls, "a second histogram request means a refinement loop"
+        calls.append(1)
+        return np.array([[inside.size]], dtype=np.int64)
+
+    ranks = [0, inside.size // 2, inside.size - 1]
+    vals, totals = exact_select(1, [lo_b], [hi_b], 1, lambda g, t: ranks, rh, rg,
+                                gather_limit=1 << 24, bucket_limit=1 << 62)
+    assert totals == [inside.size]
+    assert [vals[0][r] for r in ranks] == [inside[r] for r in ranks]
+
+    def rg_pick(lo, hi, sc, bitmap, cap, want=None):   # same protocol as PairEngine's runner
+        k, s = rg(lo, hi, sc, bitmap, cap)
+        out = {}
+        for slot, rel in want:
+            srt = np.sort(k[s == slot])
+            out[slot] = (srt.size, {r: float(srt[r]) for r in rel})
+        return out
+
+    rg_pick.device_pick = True
+    calls.clear()
+    vals2, _ = exact_select(1, [lo_b], [hi_b], 1, lambda g, t: ranks, rh, rg_pick,
+                            gather_limit=1 << 24, bucket_limit=1 << 62)
+    assert vals2[0] == vals[0]
+    # with the default bucket limit a crowded single bucket asks for a refinement: the guard trips
+    calls.clear()
+    with pytest.raises(AssertionError):
+        exact_select(1, [lo_b], [hi_b], 1, lambda g, t: ranks, rh, rg, bucket_limit=100)
