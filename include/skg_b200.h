@@ -150,6 +150,7 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
  * Replaces MetricSpace.dists + Variogram.distance + _calc_diff + _calc_groups
  * + lag_classes + estimators.matheron/cressie (MetricSpace.py:135-156,
  * Variogram.py:1202-1208, 1938-2006, 1535-1557, 2092; estimators.py:14-128).
+ *   values   [dev, n_values][n]  value columns, combined per pair as value_mode says (SKG_VALUE_*)
  *   thr_bits [host, n_lags]  bit patterns of T(edge_k), non-decreasing
  *   count    [dev, n_lags]   += pairs per lag class (exact)
  *   sum_sq   [dev, n_lags]   += sum dz^2          (if stats & SKG_STAT_SUM_SQ)
@@ -165,8 +166,9 @@ int skg_pair_dir_ambiguous(const double* coords, int64_t n, int dim, const doubl
  * spatially coherent order (Z-order, skg_morton_keys).  Each sweep first computes the
  * bounding box of every 256-point block and keeps, in ascending order, only the tiles
  * whose range of squared distances can matter: below the last lag edge (skg_pair_hist),
- * inside a segment window / possible maximum (select passes).  Exact for ANY point order
- * - an incoherent order merely culls nothing.  After a sweep the first four uint64 of
+ * inside a segment window / possible maximum (select passes) - and, with a directional
+ * mask, whose box of difference vectors can meet the azimuth cone / bandwidth strip.
+ * Exact for ANY point order - an incoherent order merely culls nothing.  After a sweep the first four uint64 of
  * `scratch` hold {surviving work items, -, j-chunks per tile (js), candidate work items};
  * a work item is 256 x (256/js) pair slots. */
 int64_t skg_pair_scratch_bytes(int64_t n, int n_lags);
