@@ -202,21 +202,27 @@ class OrdinaryKriging:
         self.singular_error = 0
         self.no_points_error = 0
         self.ill_matrix = 0
-        if len(x) != 1 or not isinstance(x[0], MetricSpace):
-            self.transform_coords = MetricSpace(np.column_stack(x).copy(), self.dist_metric, None)
+        # the per-dimension arrays go to the device as they are (SoA); the MetricSpace objects the
+        # reference builds here (Kriging.py:430-440) are formed only if somebody reads them
+        self._transform_space = None
+        if len(x) == 1 and isinstance(x[0], MetricSpace):
+            self._transform_space = x[0]
+            t = np.ascontiguousarray(np.asarray(x[0].coords, dtype=np.float64).T)
         else:
-            self.transform_coords = x[0]
-        self.transform_coords_pair = MetricSpacePair(self.transform_coords, self.coords)
-        t = np.asarray(self.transform_coords.coords, dtype=np.float64)
-        if t.shape[1] != self.coords.coords.shape[1]:
+            cols = [np.asarray(xi, dtype=np.float64).ravel() for xi in x]
+            if len({c.size for c in cols}) > 1:
+                raise ValueError("all input arrays must have the same length")
+            t = np.vstack(cols) if cols else np.zeros((0, 0))
+        self._transform_x = t
+        if t.shape[0] != self.coords.coords.shape[1]:
             raise ValueError("transform coordinates have %d dimensions, the samples %d"
-                             % (t.shape[1], self.coords.coords.shape[1]))
+                             % (t.shape[0], self.coords.coords.shape[1]))
         if self._maxp > _lib.KRIGE_MAX_POINTS:
             raise NotImplementedError("max_points > %d is not supported by the warp-per-target "
                                       "kernel yet" % _lib.KRIGE_MAX_POINTS)
         z, sigma, status = self._engine().transform(t, self._model_name, self._model_params(),
                                                     self._minp, self._maxp,
-                                                    matrix_lut=self._matrix_lut())
+                                                    matrix_lut=self._matrix_lut(), soa=True)
         self.no_points_error = int(np.count_nonzero(status == _lib.KRIGE_LESS_POINTS))
         self.singular_error = int(np.count_nonzero(status == _lib.KRIGE_SINGULAR))
         self.sigma = sigma
@@ -226,8 +232,20 @@ class OrdinaryKriging:
         if self.no_points_error > 0:
             warnings.warn("For %d locations, not enough neighbors were found within the range."
                           % self.no_points_error, KrigingWarning)
-        self.z = np.array(z)
+        self.z = z
         return np.array(z)
+
+    @property
+    def transform_coords(self):
+        """MetricSpace of the last transform's targets (Kriging.py:430-436), built on demand."""
+        if getattr(self, "_transform_space", None) is None and getattr(self, "_transform_x", None) is not None:
+            self._transform_space = MetricSpace(np.ascontiguousarray(self._transform_x.T), self.dist_metric, None)
+        return getattr(self, "_transform_space", None)
+
+    @property
+    def transform_coords_pair(self):
+        ms = self.transform_coords
+        return None if ms is None else MetricSpacePair(ms, self.coords)
 
     def __call__(self, *x):
         return self.transform(*x)

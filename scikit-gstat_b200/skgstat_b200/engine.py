@@ -1151,20 +1151,27 @@ class KrigeEngine:
         return g
 
     def transform(self, targets, model: str, model_params, min_points: int, max_points: int,
-                  exclude=None, matrix_lut=None):
-        """targets (M, dim) -> (z, sigma, status) numpy arrays for ALL M targets; with a
-        process group each rank krigs its contiguous slice and the slices are gathered."""
-        t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64))
-        if t.ndim != 2 or t.shape[1] != self.dim:
-            raise ValueError("targets must be (M, %d)" % self.dim)
-        m = int(t.shape[0])
+                  exclude=None, matrix_lut=None, soa=False):
+        """targets (M, dim) - or, with soa=True, (dim, M) as the caller's per-dimension arrays
+        already are - -> (z, sigma, status) numpy arrays for ALL M targets; with a process group
+        each rank krigs its contiguous slice and the slices are gathered."""
+        t = np.asarray(targets, dtype=np.float64)
+        if soa:
+            if t.ndim != 2 or t.shape[0] != self.dim:
+                raise ValueError("targets must be (%d, M)" % self.dim)
+            t_soa = np.ascontiguousarray(t)
+        else:
+            if t.ndim != 2 or t.shape[1] != self.dim:
+                raise ValueError("targets must be (M, %d)" % self.dim)
+            t_soa = np.ascontiguousarray(t.T)
+        m = int(t_soa.shape[1])
         mp = np.asarray(model_params, dtype=np.float64)
         if mp.size == 4:
             mp = np.concatenate((mp, [mp[0], mp[1]]))
         if mp.size != 6:
             raise ValueError("model_params = [range, sill, shape, nugget(, table range, table sill)]")
         with torch.cuda.device(self.device):
-            tg = to_device(t.T, self.device)
+            tg = to_device(t_soa, self.device)
             ex = None
             if exclude is not None:
                 ex = to_device(np.ascontiguousarray(exclude, dtype=np.int32), self.device)
