@@ -667,14 +667,24 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
         }
       };
       auto accumulate = [&](const int (&g)[HR], const double (&key)[HR]) {
+        // window test for all HR pairs first, branch-free (most in-range keys lie outside the
+        // windows: only the few that hit take the bucket / atomic path below)
+        bool inw[HR];
+        uint64_t wlo_b[HR];
 #pragma unroll
         for (int r = 0; r < HR; ++r) {
-          if (g[r] >= nb) continue;
+          const int gs = g[r] < nb ? g[r] : 0;
           const uint64_t kb = (uint64_t)__double_as_longlong(key[r]);
-          if (kb > INF_BITS) continue;  // NaN value
-          if (!SEG && !GATHER) local_max = kb > local_max ? kb : local_max;
-          if (kb < sSeg.lo_bits[g[r]] || kb >= sSeg.hi_bits[g[r]]) continue;
-          const double lo = __longlong_as_double((long long)sSeg.lo_bits[g[r]]);
+          wlo_b[r] = sSeg.lo_bits[gs];
+          const uint64_t whi_b = sSeg.hi_bits[gs];
+          const bool ok = (g[r] < nb) & (kb <= INF_BITS);   // NaN value: never counted
+          if (!SEG && !GATHER) local_max = (ok && kb > local_max) ? kb : local_max;
+          inw[r] = ok & (kb >= wlo_b[r]) & (kb < whi_b);
+        }
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          if (!inw[r]) continue;
+          const double lo = __longlong_as_double((long long)wlo_b[r]);
           long long bk = __double2ll_rz(__dmul_rn(__dsub_rn(key[r], lo), sSeg.scale[g[r]]));
           bk = bk < nbuckets - 1 ? bk : nbuckets - 1;
           const long long slot = (long long)g[r] * nbuckets + bk;
