@@ -973,6 +973,71 @@ class Variogram:
     def nrmse(self):
         return self.rmse / np.nanmean(self.experimental)
 
+    @property
+    def mean_residual(self):
+        """Variogram.py:2270-2290."""
+        return np.nanmean(np.fromiter(map(np.abs, self.model_residuals), float))
+
+    @property
+    def root_mean_square(self):
+        """Variogram.py:2328-2343."""
+        return np.sqrt(np.nanmean(np.square(self.model_residuals)))
+
+    @property
+    def residual_sum_of_squares(self):
+        """Variogram.py:2345-2359."""
+        return np.nansum(np.square(self.model_residuals))
+
+    rss = residual_sum_of_squares
+
+    @property
+    def nrmse_r(self):
+        """Variogram.py:2407-2436: rmse / (max - mean) of the experimental variogram."""
+        y = self.experimental
+        return self.rmse / (np.nanmax(y) - np.nanmean(y))
+
+    def model_deviations(self):
+        """(experimental, model at the bin edges), Variogram.py:2438-2470."""
+        exp = self.experimental
+        if self.cof is None:
+            self.fit(force=True)
+        if self.cof is None:
+            raise RuntimeError("The variogram cannot be calculated.")
+        return exp, self.transform(self.bins)
+
+    @property
+    def r(self):
+        """Pearson correlation of experimental and model values, Variogram.py:2472-2513."""
+        experimental, model = self.model_deviations()
+        mx, my = np.nanmean(experimental), np.nanmean(model)
+        term1 = np.nansum(np.fromiter(map(lambda x, y: (x - mx) * (y - my), experimental, model), float))
+        t2x = np.nansum(np.fromiter(map(lambda x: (x - mx) ** 2, experimental), float))
+        t2y = np.nansum(np.fromiter(map(lambda y: (y - my) ** 2, model), float))
+        return term1 / (np.sqrt(t2x * t2y))
+
+    pearson = r
+
+    @property
+    def NS(self):
+        """Nash-Sutcliffe efficiency of the model, Variogram.py:2515-2553."""
+        experimental, model = self.model_deviations()
+        mx = np.nanmean(experimental)
+        term1 = np.nansum(np.fromiter(map(lambda x, y: (x - y) ** 2, experimental, model), float))
+        term2 = np.nansum(np.fromiter(map(lambda x: (x - mx) ** 2, experimental), float))
+        return 1 - (term1 / term2)
+
+    def to_DataFrame(self, n=100, force=False):
+        """Variogram.py:2154-2185."""
+        from pandas import DataFrame
+        warnings.warn("The return value of this function will change in a future release.",
+                      FutureWarning)
+        lags, data = self.data(n=n, force=force)
+        return DataFrame({"lags": lags, self._model_name: data}).copy()
+
+    def update_kwargs(self, **kwargs):
+        """Variogram.py:1478-1496."""
+        self._kwargs.update(kwargs)
+
     def cross_validate(self, method="jacknife", n=None, metric="rmse", seed=None):
         """Variogram.py:2577-2625: leave-one-out kriging at the sample locations (one
         batched kernel call, see util/cross_validation.py)."""

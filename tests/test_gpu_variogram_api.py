@@ -6,7 +6,7 @@ import warnings
 
 import numpy as np
 import pytest
-from numpy.testing import assert_array_almost_equal
+from numpy.testing import assert_allclose, assert_array_almost_equal
 from scipy.spatial.distance import pdist
 
 pytestmark = pytest.mark.gpu
@@ -348,3 +348,29 @@ def test_describe_and_parameters(skg, cv30):
     d = V.describe()
     assert d["params"]["bin_func"] == "even" and d["params"]["n_lags"] == 10
     assert d["estimator"] == "matheron" and d["dist_func"] == "euclidean"
+
+
+def test_model_quality_measures_match_reference(skg):
+    """Variogram.py:2243-2553 (residual statistics, Pearson r, Nash-Sutcliffe, to_DataFrame) against the
+    reference's values on its own sample data (tests/golden/ref_quality.json, generated with the
+    reference imported from /root/reference)."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sample.npz"))
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_quality.json")))
+    for model, want in ref.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            V = skg.Variogram(g["coords"], g["values"], model=model, n_lags=12, maxlag="median")
+            got = dict(mean_residual=V.mean_residual, root_mean_square=V.root_mean_square, rss=V.rss,
+                       nrmse=V.nrmse, nrmse_r=V.nrmse_r, r=V.r, NS=V.NS, rmse=V.rmse)
+            frame = V.to_DataFrame(n=7)
+        for k, val in got.items():
+            assert_allclose(val, want[k], rtol=1e-6, err_msg="%s %s" % (model, k))
+        assert list(frame.columns) == ["lags", model]
+        assert_allclose(frame[model].values, want["frame"], rtol=1e-6)
+        exp, mod = V.model_deviations()
+        assert exp.shape == mod.shape == (12,)
+        assert V.pearson == V.r
+    V.update_kwargs(percentile=25)
+    assert V._kwargs["percentile"] == 25
