@@ -515,6 +515,24 @@ def make_sparse(skg, ds):
     print("sparse cases:", len(manifest))
 
 
+def make_quality(skg):
+    """Model quality measures of the reference (Variogram.py:2243-2553) on its own sample data
+    (tests/sample.csv -> tests/golden/ref_sample.npz)."""
+    z = np.load(os.path.join(OUT, "ref_sample.npz"))
+    c, v = z["coords"], z["values"]
+    out = {}
+    for model in ("spherical", "exponential", "gaussian"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            V = skg.Variogram(c, v, model=model, n_lags=12, maxlag="median")
+            out[model] = dict(mean_residual=float(V.mean_residual), root_mean_square=float(V.root_mean_square),
+                              rss=float(V.rss), nrmse=float(V.nrmse), nrmse_r=float(V.nrmse_r), r=float(V.r),
+                              NS=float(V.NS), rmse=float(V.rmse),
+                              frame=[float(x) for x in V.to_DataFrame(n=7)[model].values])
+    with open(os.path.join(OUT, "ref_quality.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
 def make_api_fixture(skg):
     """The reference's own test fixture tests/sample.csv (200 rows x, y, z), used by
     test_variogram.py::test_fit_lm; data only."""
@@ -528,7 +546,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     skg = import_reference()
     ds = datasets(skg)
-    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners", "estimators", "sparse"]
+    which = sys.argv[1:] or ["variogram", "directional", "kriging", "cv", "api", "multivariate", "kriging_ext", "binners", "estimators", "sparse", "quality"]
     if "variogram" in which:
         make_variogram(skg, ds)
     if "directional" in which:
@@ -549,6 +567,8 @@ def main():
         make_estimators(skg, ds)
     if "sparse" in which:
         make_sparse(skg, ds)
+    if "quality" in which:
+        make_quality(skg)
 
 
 if __name__ == "__main__":
