@@ -280,8 +280,8 @@ def run_own(args):
                          "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this
                          # config, from the committed ncu --set full capture
-                         # (profiles/r1_pair_hist_ncu_summary.txt); algorithmic bytes: 480 600
-                         "traffic": 514816 if world == 1 else None,
+                         # (profiles/r1_pair_hist_ncu_summary.txt: 590 592 B read, 0 written); algorithmic bytes: 480 600
+                         "traffic": 590592 if world == 1 else None,
                          "kernel": "pair_hist_kernel<2,0,1,1,true>", "kernel_ms": kern_ms,
                          "pairs_evaluated": evaluated, "pairs_total": my_pairs,
                          "culled_fraction": 1.0 - evaluated / my_pairs,
