@@ -93,7 +93,18 @@ def uniform_count_lags(d: np.ndarray, n: int, maxlag):
     )
 
 
+def auto_derived_lags(d: np.ndarray, method_name: str, maxlag):
+    """binning.py:82-122: np.histogram_bin_edges rules ('sqrt', 'sturges', 'rice', 'scott',
+    'doane', 'fd', 'auto') on the distances up to maxlag."""
+    if maxlag is None or maxlag > np.nanmax(d):
+        maxlag = np.nanmax(d)
+    dd = d[np.where(d <= maxlag)]
+    return np.histogram_bin_edges(dd, bins=method_name)[1:]
+
+
+AUTO_BINNERS = ("sqrt", "sturges", "rice", "scott", "doane", "fd", "auto")
 BIN_FUNCS = {"even": even_width_lags, "uniform": uniform_count_lags}
+BIN_FUNCS.update({m: (lambda d, n, ml, m=m: auto_derived_lags(d, m, ml)) for m in AUTO_BINNERS})
 
 
 def lag_groups(d: np.ndarray, edges: np.ndarray) -> np.ndarray:
@@ -127,23 +138,61 @@ def dowd(x: np.ndarray) -> float:
     return 2.198 * np.nanmedian(x) ** 2 / 2
 
 
-ESTIMATORS = {"matheron": matheron, "cressie": cressie, "dowd": dowd}
+def minmax(x: np.ndarray) -> float:
+    """estimators.py:296."""
+    return (np.nanmax(x) - np.nanmin(x)) / np.nanmean(x)
+
+
+def percentile(x: np.ndarray, p=50) -> float:
+    """estimators.py:324."""
+    return np.percentile(x, q=p)
+
+
+def shannon_entropy(x: np.ndarray, bins) -> float:
+    """util/shannon.py:27-34 (estimators.entropy, estimators.py:327-367)."""
+    c, _ = np.histogram(x, bins=bins)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = c / np.sum(c) + 1e-15
+    return -np.fromiter(map(np.log2, p), dtype=float).dot(p)
+
+
+ESTIMATORS = {"matheron": matheron, "cressie": cressie, "dowd": dowd, "minmax": minmax,
+              "percentile": percentile}
 
 
 def dense_variogram(coordinates, values, estimator="matheron", bin_func="even",
-                    n_lags=10, maxlag=None, multivariate=None):
+                    n_lags=10, maxlag=None, multivariate=None, max_dist=None, **kwargs):
     """Variogram.py:31-405 (constructor) restricted to the experimental part:
     returns dict(maxlag, bins, bin_count, experimental).  multivariate: None (1-D values),
-    'cross' or 'aggregate' (2-D values)."""
+    'cross' or 'aggregate' (2-D values).  max_dist: sparse MetricSpace (MetricSpace.py:141-147,
+    Variogram.py:1210-1227) - only the pairs with 0 < d <= max_dist exist.  kwargs: 'percentile'
+    and 'entropy_bins' as Variogram.py:2065-2082 reads them."""
     d = distance(coordinates)
     if multivariate is None:
         diffs = pairwise_diffs(np.asarray(values, dtype=float))
     else:
         diffs = pairwise_diffs_multi(values, multivariate)
+    if max_dist is not None:
+        # the reference's sparse vectors hold the lower-triangle entries row by row
+        # (Variogram.py:1210-1227), i.e. the pairs (i < j) ordered by j, then i - the order
+        # matters for np.mean's pairwise summation (maxlag='mean')
+        keep = np.flatnonzero((d > 0) & (d <= max_dist))
+        iu, ju = np.triu_indices(len(np.asarray(coordinates)), 1)
+        keep = keep[np.lexsort((iu[keep], ju[keep]))]
+        d, diffs = d[keep], diffs[keep]
     ml = resolve_maxlag(d, maxlag)
     edges = BIN_FUNCS[bin_func](d, n_lags, ml)
     g = lag_groups(d, edges)
-    est = ESTIMATORS[estimator]
+    if estimator == "entropy":          # Variogram.py:2065-2075: edges from the DISTANCE vector
+        nb = kwargs.get("entropy_bins", 50)
+        if isinstance(nb, int):
+            nb -= 1
+        vbins = np.histogram_bin_edges(d, bins=nb)
+        est = lambda x: shannon_entropy(x, vbins)
+    elif estimator == "percentile" and kwargs.get("percentile", False):
+        est = lambda x: percentile(x, kwargs["percentile"])
+    else:
+        est = ESTIMATORS[estimator]
     # Variogram.py:1556-1557 / 2092: one boolean sweep per lag class
     classes = [diffs[np.where(g == i)] for i in range(len(edges))]
     return dict(
