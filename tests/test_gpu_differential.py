@@ -162,3 +162,47 @@ def test_random_directional_configurations_match_the_oracle(skg):
                             err_msg=msg)
         done += 1
     assert done >= 40
+
+
+def test_random_rule_binners_estimators_and_sparse_spaces_match_the_oracle(skg):
+    """Random configurations over the histogram-rule binners, the minmax / percentile / entropy
+    estimators and sparse (max_dist) spaces."""
+    rng = np.random.default_rng(99)
+    done = 0
+    for it in range(90):
+        n = int(rng.choice([30, 120, 256, 400, 777]))
+        dim = int(rng.choice([2, 2, 3]))
+        c = rng.random((n, dim)) * 100.0
+        if rng.random() < 0.25:
+            c[rng.integers(0, n, size=3)] = c[0]
+        v = rng.normal(size=n) * 3.0 + 10.0
+        est = str(rng.choice(["matheron", "cressie", "dowd", "minmax", "percentile", "entropy"]))
+        bf = str(rng.choice(["even", "uniform", "sturges", "scott", "doane", "fd", "rice", "auto"]))
+        n_lags = int(rng.choice([5, 10, 20]))
+        ml = {0: None, 1: "median", 2: 0.45}[int(rng.integers(0, 3))]
+        md = None if rng.random() < 0.5 else float(rng.choice([25.0, 60.0, 500.0]))
+        kw = {}
+        if est == "percentile" and rng.random() < 0.5:
+            kw["percentile"] = float(rng.choice([10, 33.3, 75]))
+        if est == "entropy" and rng.random() < 0.5:
+            kw["entropy_bins"] = int(rng.choice([12, 30]))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                with np.errstate(all="ignore"):
+                    ref = ov.dense_variogram(c, v, est, bf, n_lags, ml, max_dist=md, **kw)
+            except Exception:
+                continue    # the reference raises here (e.g. minmax / percentile of an empty lag class)
+            edges = np.asarray(ref["bins"], dtype=float)
+            if edges.size == 0 or edges.size > 240 or np.any(np.diff(edges) < 0) or not np.all(np.isfinite(edges)):
+                continue
+            coords = c if md is None else skg.MetricSpace(c, max_dist=md)
+            V = skg.Variogram(coords, v, estimator=est, bin_func=bf, n_lags=n_lags, maxlag=ml, fit_method=None, **kw)
+            msg = "iteration %d: n=%d dim=%d est=%s bf=%s n_lags=%d maxlag=%r max_dist=%r %r" % (
+                it, n, dim, est, bf, n_lags, ml, md, kw)
+            assert_array_equal(V.bins, ref["bins"], err_msg=msg)
+            assert_array_equal(V.bin_count, ref["bin_count"], err_msg=msg)
+            assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, atol=1e-300, equal_nan=True,
+                            err_msg=msg)
+        done += 1
+    assert done >= 50
