@@ -545,6 +545,10 @@ class Variogram:
             hist = eng.dz_value_histogram(edges, value_edges, dirp, thr_bits=thr)
             cnt = eng.hist_counts(thr, dirp)
             exp = np.array([estimators.shannon_from_counts(hist[g]) for g in range(len(edges))])
+        if name in ("dowd", "minmax", "percentile") and not np.isfinite(np.asarray(self._values, dtype=float)).all():
+            # the order-statistic passes count finite differences only; a lag class's size
+            # (bin_count, Variogram.py:942-947) includes the pairs of NaN observations
+            cnt = eng.hist_counts(thr, dirp)
         return np.asarray(cnt, dtype=np.int64), np.asarray(exp, dtype=float)
 
     def experimental_batch(self, values):

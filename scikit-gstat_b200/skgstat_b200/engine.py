@@ -944,7 +944,10 @@ class PairEngine:
             return [] if tot == 0 else [(tot - 1) // 2, tot // 2]
 
         totals = med_lo = med_hi = None
-        if self.n_pairs >= self.WINDOWED_MEDIAN_MIN_PAIRS and nl * 16 * 64 <= 180 * 1024:
+        # NaN observations: np.nanmedian ranks only the finite differences, which the windowed
+        # path's pair counts cannot tell apart -> plain select over the finite keys
+        finite_values = bool(np.isfinite(self._orig_values).all())
+        if finite_values and self.n_pairs >= self.WINDOWED_MEDIAN_MIN_PAIRS and nl * 16 * 64 <= 180 * 1024:
             win = self._median_windows(thr, dirp, hi)
             if win is not None:
                 w_lo, w_hi = win                      # per-lag bit windows [lo, hi)

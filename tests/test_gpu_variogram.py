@@ -236,3 +236,20 @@ def test_windowed_select_paths_are_exact(skg, monkeypatch):
     assert_array_equal(V.bins, ref["bins"])
     assert_array_equal(V.bin_count, ref["bin_count"])
     assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, equal_nan=True)
+
+
+def test_nan_observations_follow_numpy_nan_rules(skg):
+    """NaN values: matheron / cressie propagate NaN like np.sum, dowd uses np.nanmedian
+    (estimators.py:178) and bin_count still counts every pair of the lag class."""
+    c = random_points(700, 100.0, 2, seed=31)
+    v = gaussian_field(c, 10.0, seed=31)
+    v[[5, 77, 300]] = np.nan
+    for est in ("matheron", "dowd"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = ov.dense_variogram(c, v, est, "even", 10, "median")
+            V = skg.Variogram(c, v, estimator=est, n_lags=10, maxlag="median", fit_method=None)
+            exp = V.experimental
+        assert_array_equal(V.bins, ref["bins"])
+        assert_array_equal(V.bin_count, ref["bin_count"])
+        assert_allclose(exp, ref["experimental"], rtol=1e-12, equal_nan=True)
