@@ -60,6 +60,16 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1
     with pytest.raises(_lib.SkgError):
         _lib.check(rc, "skg_krige")
+    # the newer entry points validate before touching the device too
+    rc = lib.skg_pair_hist_batch(None, None, 4, 10, 2, None, thr.ctypes.data_as(C.c_void_p), 3, 1,
+                                 None, None, None, 0, 0, 0, 1, None)
+    assert rc == -1 and b"NULL" in lib.skg_last_error()
+    rc = lib.skg_pair_cell_counts(None, 10, 2, None, 0, 1 << 62, 11, 0, None, None, 0, 0, 0, 1, None)
+    assert rc == -1
+    rc = lib.skg_pair_hist(C.c_void_p(8), C.c_void_p(8), 3, 1, 10, 2, None, thr.ctypes.data_as(C.c_void_p),
+                           3, 1, None, C.c_void_p(8), C.c_void_p(8), None, None, 0, 0, 0, 1, None)
+    assert rc == -1 and b"cross 2" in lib.skg_last_error()   # "scalar needs 1 column, cross 2, ..."
+    assert lib.skg_pair_batch_max_lags() >= 64
 
 
 def test_no_cpu_fallback_without_cuda():
