@@ -109,24 +109,40 @@ __device__ __forceinline__ void sweep_tiles(const double* __restrict__ coords,
 template <int DIM>
 __global__ void __launch_bounds__(256)
 block_bbox_kernel(const double* __restrict__ coords, int64_t n, double* __restrict__ bbox,
-                  double* __restrict__ bbox32) {
+                  double* __restrict__ bbox32, double* __restrict__ bbox8) {
   __shared__ double sLo[DIM][8], sHi[DIM][8];
   const int64_t i = (int64_t)blockIdx.x * TILE + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double inf = __longlong_as_double((long long)INF_BITS);
+  bool bad = i >= n;  // NaN coordinate or padding: the point's 8-group gets no usable box
 #pragma unroll
   for (int k = 0; k < DIM; ++k) {
     const double v = i < n ? coords[(int64_t)k * n + i] : __longlong_as_double(NAN_BITS);
+    bad |= !(v == v);
     double lo = (v == v) ? v : inf, hi = (v == v) ? v : -inf;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
       lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      if (o == 4 && DIM == 2 && bbox8 && (lane & 7) == 0) {  // boxes of the aligned 8-point groups
+        const int64_t g8 = (int64_t)blockIdx.x * (TILE / 8) + (threadIdx.x >> 3);
+        bbox8[g8 * 4 + k] = lo;
+        bbox8[g8 * 4 + 2 + k] = hi;
+      }
     }
     if (lane == 0) {
       sLo[k][warp] = lo; sHi[k][warp] = hi;
       bbox32[((int64_t)blockIdx.x * 8 + warp) * 6 + k] = lo;      // 32-point sub-block boxes
       bbox32[((int64_t)blockIdx.x * 8 + warp) * 6 + 3 + k] = hi;
+    }
+  }
+  if (DIM == 2 && bbox8) {
+    // a group with a NaN / missing point is flagged by a NaN lower x: every window test on it
+    // fails and its pairs take the per-pair path
+    const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+    if ((lane & 7) == 0 && ((badmask >> lane) & 0xffu)) {
+      const int64_t g8 = (int64_t)blockIdx.x * (TILE / 8) + (threadIdx.x >> 3);
+      bbox8[g8 * 4] = __longlong_as_double(NAN_BITS);
     }
   }
   __syncthreads();
@@ -161,94 +177,125 @@ __global__ void tile_need_kernel(const double* __restrict__ bbox, int64_t nt, in
   if ((threadIdx.x & 31) == 0) atomicMax(&counters[1], (unsigned long long)__double_as_longlong(m));
 }
 
-template <int DIM>
-__global__ void item_flags_kernel(const double* __restrict__ bbox, const double* __restrict__ bbox32,
-                                  int64_t n, int64_t nt, int64_t t_begin, int64_t ntile,
-                                  int64_t t_stride, int js, const __grid_constant__ CullWindows win,
-                                  const unsigned long long* __restrict__ counters,
-                                  unsigned char* __restrict__ flags) {
-  const int64_t nitem = ntile * js;
-  const int jchunk = TILE / js;
-  const double need = win.want_max
-      ? __longlong_as_double((long long)counters[1]) * (1.0 - 1e-12) : 0.0;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nitem;
-       k += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = t_begin + (k / js) * t_stride;
-    const int h = (int)(k % js);
-    int I, J;
-    tile_decode(t, nt, I, J);
-    int keep = 0;
-    if ((int64_t)J * TILE + (int64_t)h * jchunk < n) {  // the chunk holds points
-      double jb[6], a, b;
-      chunk_box<DIM>(bbox32, J, h, js, jb);
-      subblock_range<DIM>(bbox, I, jb, a, b);
-      if (a == a && b == b && a <= b) {
-        const double lo = a * (1.0 - 1e-12), hi = b * (1.0 + 1e-12);
-        for (int w = 0; w < win.count; ++w) keep |= (lo < win.hi[w] && hi >= win.lo[w]) ? 1 : 0;
-        if (win.want_max && hi >= need) keep = 1;
-        if (DIM == 2 && keep && win.dir_model != SKG_DIR_NONE &&
-            !dir_box_may_pass(bbox + (int64_t)I * 6, jb, win))
-          keep = 0;
-      }
-    }
-    flags[k] = (unsigned char)keep;
-  }
-}
+// Flags + ORDERED compaction in one launch.  A CTA takes the next block of CULL_ITEMS work items
+// (atomic ticket, so a block only ever waits for blocks that are already running), decides
+// their flags, scans them and finds its output offset by decoupled look-back over the
+// published per-block aggregates / inclusive prefixes; the list comes out in ascending item
+// order, hence the sweep's static round-robin and fixed-order reductions stay deterministic.
+constexpr int CULL_THREADS = 256;
+constexpr int CULL_PER_THREAD = 8;
+constexpr int CULL_ITEMS = CULL_THREADS * CULL_PER_THREAD;
+constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PREFIX = 2ull << 62, SCAN_VAL = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(1024)
-item_compact_kernel(const unsigned char* __restrict__ flags, int64_t t_begin, int64_t ntile,
-                    int64_t t_stride, int js, unsigned int* __restrict__ list,
-                    unsigned long long* __restrict__ counters) {
-  __shared__ int warp_tot[32];
-  __shared__ long long carry;
+template <int DIM>
+__global__ void __launch_bounds__(CULL_THREADS)
+item_cull_kernel(const double* __restrict__ bbox, const double* __restrict__ bbox32, int64_t n,
+                 int64_t nt, int64_t t_begin, int64_t ntile, int64_t t_stride, int js,
+                 const __grid_constant__ CullWindows win, unsigned long long* __restrict__ counters,
+                 unsigned long long* __restrict__ scan /* [0] ticket, [1 + b] block status */,
+                 unsigned int* __restrict__ list) {
+  __shared__ int warp_tot[CULL_THREADS / 32];
+  __shared__ long long s_base;
+  __shared__ unsigned int s_block;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t nitem = ntile * js;
-  if (tid == 0) carry = 0;
+  const int jchunk = TILE / js;
+  if (tid == 0) s_block = (unsigned int)atomicAdd(&scan[0], 1ull);
   __syncthreads();
-  for (int64_t base = 0; base < nitem; base += 4096) {
-    const int64_t k0 = base + (int64_t)tid * 4;
-    int f[4], cnt = 0;
+  const int64_t blk = s_block;
+  const double need = win.want_max
+      ? __longlong_as_double((long long)counters[1]) * (1.0 - 1e-12) : 0.0;
+  const int64_t k0 = blk * CULL_ITEMS + (int64_t)tid * CULL_PER_THREAD;
+  unsigned int items[CULL_PER_THREAD];
+  unsigned keepmask = 0u;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      f[q] = (k0 + q < nitem) ? flags[k0 + q] : 0;
-      cnt += f[q];
-    }
-    int x = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_tot[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int v = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += y;
-      }
-      warp_tot[lane] = v;
-    }
-    __syncthreads();
-    long long pos = carry + (warp ? warp_tot[warp - 1] : 0) + (x - cnt);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (f[q]) {
-        const int64_t k = k0 + q;
-        const int64_t t = t_begin + (k / js) * t_stride;
-        list[pos++] = (unsigned int)(t * js + (k % js));
+  for (int q = 0; q < CULL_PER_THREAD; ++q) {
+    const int64_t k = k0 + q;
+    int keep = 0;
+    items[q] = 0u;
+    if (k < nitem) {
+      const int64_t t = t_begin + (k / js) * t_stride;
+      const int h = (int)(k % js);
+      items[q] = (unsigned int)(t * js + h);
+      int I, J;
+      tile_decode(t, nt, I, J);
+      if ((int64_t)J * TILE + (int64_t)h * jchunk < n) {  // the chunk holds points
+        double jb[6], a, b;
+        chunk_box<DIM>(bbox32, J, h, js, jb);
+        subblock_range<DIM>(bbox, I, jb, a, b);
+        if (a == a && b == b && a <= b) {
+          const double lo = a * (1.0 - 1e-12), hi = b * (1.0 + 1e-12);
+          for (int w = 0; w < win.count; ++w) keep |= (lo < win.hi[w] && hi >= win.lo[w]) ? 1 : 0;
+          if (win.want_max && hi >= need) keep = 1;
+          if (DIM == 2 && keep && win.dir_model != SKG_DIR_NONE &&
+              !dir_box_may_pass(bbox + (int64_t)I * 6, jb, win))
+            keep = 0;
+        }
       }
     }
-    __syncthreads();
-    if (tid == blockDim.x - 1) carry = pos;
-    __syncthreads();
+    keepmask |= (unsigned)keep << q;
   }
-  if (tid == 0) {
-    counters[0] = (unsigned long long)carry;  // surviving work items
-    counters[2] = (unsigned long long)js;     // j-chunks per tile (for reporting)
-    counters[3] = (unsigned long long)nitem;  // candidate work items before culling
+  const int cnt = __popc(keepmask);
+  int x = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
   }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < CULL_THREADS / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < CULL_THREADS / 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += y;
+    }
+    if (lane < CULL_THREADS / 32) warp_tot[lane] = v;
+    const long long total = __shfl_sync(0xffffffffu, v, CULL_THREADS / 32 - 1);
+    // publish the aggregate, then look back for the exclusive prefix
+    volatile unsigned long long* st = scan + 1;
+    long long excl = 0;
+    if (blk == 0) {
+      if (lane == 0) { st[0] = SCAN_PREFIX | (unsigned long long)total; }
+    } else {
+      if (lane == 0) { st[blk] = SCAN_AGG | (unsigned long long)total; }
+      __threadfence();
+      int64_t j = blk - 1;
+      while (true) {  // 32 predecessors per step, newest first
+        const int64_t idx = j - lane;
+        unsigned long long v2 = SCAN_PREFIX;  // lanes below block 0 act as an empty prefix
+        if (idx >= 0) {
+          do { v2 = st[idx]; } while ((v2 >> 62) == 0ull);
+        }
+        const unsigned pref = __ballot_sync(0xffffffffu, (v2 >> 62) == 2ull);
+        const int first = pref ? (__ffs(pref) - 1) : 32;       // nearest block with a full prefix
+        long long add = (lane <= first) ? (long long)(v2 & SCAN_VAL) : 0ll;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+        excl += add;
+        if (pref) break;
+        j -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        st[blk] = SCAN_PREFIX | (unsigned long long)(excl + total);
+      }
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if ((blk + 1) * CULL_ITEMS >= nitem) {  // the last block knows the grand total
+        counters[0] = (unsigned long long)(excl + total);  // surviving work items
+        counters[2] = (unsigned long long)js;              // j-chunks per tile (for reporting)
+        counters[3] = (unsigned long long)nitem;           // candidate work items before culling
+      }
+    }
+  }
+  __syncthreads();
+  long long pos = s_base + (warp ? warp_tot[warp - 1] : 0) + (x - cnt);
+#pragma unroll
+  for (int q = 0; q < CULL_PER_THREAD; ++q)
+    if ((keepmask >> q) & 1u) list[pos++] = items[q];
 }
 
 
@@ -491,10 +538,13 @@ constexpr int64_t LIST_SPLIT_CAP = 1 << 22;  // j-splitting only while tiles * j
 
 static int64_t list_entries(int64_t ntiles) { return std::max<int64_t>(ntiles, std::min<int64_t>(ntiles * 16, LIST_SPLIT_CAP)); }
 
+static int64_t scan_entries(int64_t ntiles) { return list_entries(ntiles) / CULL_ITEMS + 4; }
+
 int64_t sweep_head_bytes(int64_t n) {
   const int64_t nt = (n + TILE - 1) / TILE;
   const int64_t ntiles = nt * (nt + 1) / 2;
-  int64_t b = 256 + nt * 6 * 8 + nt * 8 * 6 * 8 + list_entries(ntiles) * 5;
+  int64_t b = 256 + nt * 6 * 8 + nt * 8 * 6 * 8 + nt * (TILE / 8) * 4 * 8 + scan_entries(ntiles) * 8 +
+              list_entries(ntiles) * 4;
   return (b + 255) & ~255ll;
 }
 
@@ -506,12 +556,15 @@ int carve_scratch(void* scratch, int64_t scratch_bytes, int64_t n, int64_t need_
     return SKG_E_SCRATCH;
   }
   const int64_t nt = (n + TILE - 1) / TILE;
+  const int64_t ntiles = nt * (nt + 1) / 2;
   unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
   out->counters = reinterpret_cast<unsigned long long*>(base);
   out->bbox = reinterpret_cast<double*>(base + 256);
-  out->bbox32 = reinterpret_cast<double*>(base + 256 + nt * 6 * 8);
-  out->list = reinterpret_cast<unsigned int*>(base + 256 + nt * 6 * 8 + nt * 8 * 6 * 8);
-  out->flags = reinterpret_cast<unsigned char*>(out->list) + list_entries(nt * (nt + 1) / 2) * 4;
+  out->bbox32 = out->bbox + nt * 6;
+  out->bbox8 = out->bbox32 + nt * 8 * 6;
+  out->scan = reinterpret_cast<unsigned long long*>(out->bbox8 + nt * (TILE / 8) * 4);
+  out->scan_bytes = scan_entries(ntiles) * 8;
+  out->list = reinterpret_cast<unsigned int*>(out->scan + scan_entries(ntiles));
   out->tail = base + head;
   out->tail_bytes = scratch_bytes - head;
   return 0;
@@ -537,21 +590,23 @@ int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win
   const int64_t nt = (n + TILE - 1) / TILE;
   const int64_t ntile = t1 > t0 ? (t1 - t0 + stride - 1) / stride : 0;
   const int64_t nitem = ntile * js;
-  const unsigned fb = (unsigned)std::min<int64_t>((nitem + 255) / 256, (int64_t)sm_count() * 8);
   const unsigned tb = (unsigned)std::min<int64_t>((ntile + 255) / 256, (int64_t)sm_count() * 8);
-  if (win.want_max) SKG_CUDA(cudaMemsetAsync(S.counters + 1, 0, 8, st));
+  const int64_t cb = (nitem + CULL_ITEMS - 1) / CULL_ITEMS;
+  // counters[0..7] (list length, max bits, js, nitem, window group size, ...) + ticket/status
+  SKG_CUDA(cudaMemsetAsync(S.counters, 0, 128, st));
+  SKG_CUDA(cudaMemsetAsync(S.scan, 0, (size_t)std::min<int64_t>(S.scan_bytes, (cb + 1) * 8), st));
+  if (nitem == 0) return 0;
   if (dim == 3) {
-    block_bbox_kernel<3><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32);
+    block_bbox_kernel<3><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32, nullptr);
     if (win.want_max) tile_need_kernel<3><<<tb, 256, 0, st>>>(S.bbox, nt, t0, ntile, stride, S.counters);
-    item_flags_kernel<3><<<fb, 256, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride, js, win,
-                                             S.counters, S.flags);
+    item_cull_kernel<3><<<(unsigned)cb, CULL_THREADS, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride,
+                                                              js, win, S.counters, S.scan, S.list);
   } else {
-    block_bbox_kernel<2><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32);
+    block_bbox_kernel<2><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32, S.bbox8);
     if (win.want_max) tile_need_kernel<2><<<tb, 256, 0, st>>>(S.bbox, nt, t0, ntile, stride, S.counters);
-    item_flags_kernel<2><<<fb, 256, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride, js, win,
-                                             S.counters, S.flags);
+    item_cull_kernel<2><<<(unsigned)cb, CULL_THREADS, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride,
+                                                              js, win, S.counters, S.scan, S.list);
   }
-  item_compact_kernel<<<1, 1024, 0, st>>>(S.flags, t0, ntile, stride, js, S.list, S.counters);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -766,7 +821,21 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
   if (stats == SKG_STAT_COUNT_BELOW)
     for (int k = 0; k < n_lags; ++k) dzt.lo[k] = dz_lo[k];
   HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, S.bbox, S.bbox32,
-               win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks, mv};
+               win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks, mv, S.bbox8};
+  // register lag windows: 2-D isotropic sweeps over scalar values with an estimator sum
+  const bool win_off = getenv("SKG_WIN_OFF") != nullptr;  // developer switch: first kernel only
+  if (!win_off && dim == 2 && dp.model == SKG_DIR_NONE && !use_mv && stats >= 1 && stats <= 3) {
+    L.smem = hist_win_smem_bytes(n_lags, stats);
+    if (L.smem <= 160 * 1024) {
+      rc = dispatch_hist_win(tab.emax, stats, L);
+      if (rc) return rc;
+      pair_hist_reduce_kernel<<<n_lags, 32, 0, st>>>(
+          partial, nblocks, n_lags, reinterpret_cast<unsigned long long*>(count),
+          (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr, (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr);
+      SKG_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   bool priv = true;
   L.smem = hist_smem_bytes(n_lags, stats, true) + (use_mv ? mv_smem_bytes(mv) : 0);
   if (L.smem > 180 * 1024) {

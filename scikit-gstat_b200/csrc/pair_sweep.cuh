@@ -75,8 +75,10 @@ struct SweepScratch {  // views into the caller's scratch buffer
   unsigned long long* counters;  // [0] = number of listed tiles
   double* bbox;                  // [nt][6]: lo x,y,w ; hi x,y,w
   double* bbox32;                // [nt*8][6]: boxes of the 32-point sub-blocks
+  double* bbox8;                 // [nt*32][4]: lo x, lo y, hi x, hi y of the 8-point groups (2-D)
+  unsigned long long* scan;      // [0] block ticket, [1 + b] look-back status of the ordered compaction
+  int64_t scan_bytes;
   unsigned int* list;            // surviving work items, ascending
-  unsigned char* flags;          // one byte per candidate work item
   unsigned char* tail;           // kernel-specific remainder (hist partials)
   int64_t tail_bytes;
 };
@@ -742,6 +744,7 @@ struct HistLaunch {
   const double* bbox; const double* bbox32; double wlo, whi; const DzTable* dzt;
   int max_blocks; int64_t ntiles; int js; size_t smem; cudaStream_t st; int* nblocks_out;
   MvSpec mv;
+  const double* bbox8;
 };
 
 template <int DIM, int DIR, int STATS, int EMAX, bool PRIV, bool VM>
@@ -808,6 +811,8 @@ int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win
 // dir: 0 none, 1 mask with guard-band pairs excluded, 2 literal mask on the device
 int dispatch_hist(bool priv, int emax, int dim, int dir, int stats, const HistLaunch& L);   // pair_kernels.cu
 int dispatch_hist_mv(int dim, int dir, int stats, const HistLaunch& L);                      // pair_mv.cu
+int dispatch_hist_win(int emax, int stats, const HistLaunch& L);                              // pair_win.cu
+size_t hist_win_smem_bytes(int nb, int stats);
 int dispatch_select(bool gather, int dim, int dir, bool seg, int key, const SelectLaunch& L);  // pair_select.cu
 int dispatch_select_mv(bool gather, int dim, int dir, const SelectLaunch& L);                // pair_mv.cu
 

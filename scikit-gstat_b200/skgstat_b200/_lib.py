@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libskg_b200.so")
+LIB_PATH = os.environ.get("SKG_B200_LIB") or os.path.join(_HERE, "libskg_b200.so")  # env: developer builds
 
 ABI_VERSION = 4
 TILE = 256
