@@ -187,13 +187,21 @@ constexpr int CULL_PER_THREAD = 8;
 constexpr int CULL_ITEMS = CULL_THREADS * CULL_PER_THREAD;
 constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PREFIX = 2ull << 62, SCAN_VAL = (1ull << 62) - 1;
 
+// Count-only sweeps: a work item whose whole range of squared distances lies in ONE class is
+// counted here in bulk (rows x columns, no pair is ever evaluated) and dropped from the list.
+struct BulkTable {
+  int nb;              // 0 = off
+  double thr[THR_MAX];  // class thresholds as doubles
+};
+
 template <int DIM>
 __global__ void __launch_bounds__(CULL_THREADS)
 item_cull_kernel(const double* __restrict__ bbox, const double* __restrict__ bbox32, int64_t n,
                  int64_t nt, int64_t t_begin, int64_t ntile, int64_t t_stride, int js,
                  const __grid_constant__ CullWindows win, unsigned long long* __restrict__ counters,
                  unsigned long long* __restrict__ scan /* [0] ticket, [1 + b] block status */,
-                 unsigned int* __restrict__ list) {
+                 unsigned int* __restrict__ list, const __grid_constant__ BulkTable bulk,
+                 unsigned long long* __restrict__ bulk_count) {
   __shared__ int warp_tot[CULL_THREADS / 32];
   __shared__ long long s_base;
   __shared__ unsigned int s_block;
@@ -230,6 +238,26 @@ item_cull_kernel(const double* __restrict__ bbox, const double* __restrict__ bbo
           if (DIM == 2 && keep && win.dir_model != SKG_DIR_NONE &&
               !dir_box_may_pass(bbox + (int64_t)I * 6, jb, win))
             keep = 0;
+          if (keep && bulk.nb > 0 && I != J) {
+            // class(v) = #{k : thr[k] <= v}; the 1e-12 slack covers the rounding of the box arithmetic
+            int c0 = 0, c1 = 0;
+            for (int sidx = 0, len = bulk.nb; len > 0;) {  // lower class bound by bisection
+              const int half = len >> 1;
+              if (bulk.thr[sidx + half] <= lo) { sidx += half + 1; len -= half + 1; } else len = half;
+              c0 = sidx;
+            }
+            for (int sidx = 0, len = bulk.nb; len > 0;) {
+              const int half = len >> 1;
+              if (bulk.thr[sidx + half] <= hi) { sidx += half + 1; len -= half + 1; } else len = half;
+              c1 = sidx;
+            }
+            if (c0 == c1) {
+              const int64_t rows = min((int64_t)TILE, n - (int64_t)I * TILE);
+              const int64_t cols = min((int64_t)jchunk, n - ((int64_t)J * TILE + (int64_t)h * jchunk));
+              if (c0 < bulk.nb) atomicAdd(&bulk_count[c0], (unsigned long long)(rows * cols));
+              keep = 0;
+            }
+          }
         }
       }
     }
@@ -586,7 +614,13 @@ int choose_js(int64_t tiles) {
 
 int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win,
                 int64_t t0, int64_t t1, int64_t stride, int js, const SweepScratch& S,
-                cudaStream_t st) {
+                cudaStream_t st, const BinTable* bulk_tab, unsigned long long* bulk_count) {
+  BulkTable bulk;  // passed to the kernel by value
+  bulk.nb = 0;
+  if (bulk_tab && bulk_count) {
+    bulk.nb = bulk_tab->nb;
+    for (int k = 0; k < bulk_tab->nb; ++k) std::memcpy(&bulk.thr[k], &bulk_tab->thr[k], 8);
+  }
   const int64_t nt = (n + TILE - 1) / TILE;
   const int64_t ntile = t1 > t0 ? (t1 - t0 + stride - 1) / stride : 0;
   const int64_t nitem = ntile * js;
@@ -600,12 +634,14 @@ int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win
     block_bbox_kernel<3><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32, nullptr);
     if (win.want_max) tile_need_kernel<3><<<tb, 256, 0, st>>>(S.bbox, nt, t0, ntile, stride, S.counters);
     item_cull_kernel<3><<<(unsigned)cb, CULL_THREADS, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride,
-                                                              js, win, S.counters, S.scan, S.list);
+                                                              js, win, S.counters, S.scan, S.list, bulk,
+                                                              bulk_count);
   } else {
     block_bbox_kernel<2><<<(unsigned)nt, 256, 0, st>>>(coords, n, S.bbox, S.bbox32, S.bbox8);
     if (win.want_max) tile_need_kernel<2><<<tb, 256, 0, st>>>(S.bbox, nt, t0, ntile, stride, S.counters);
     item_cull_kernel<2><<<(unsigned)cb, CULL_THREADS, 0, st>>>(S.bbox, S.bbox32, n, nt, t0, ntile, stride,
-                                                              js, win, S.counters, S.scan, S.list);
+                                                              js, win, S.counters, S.scan, S.list, bulk,
+                                                              bulk_count);
   }
   SKG_CUDA(cudaGetLastError());
   return 0;
@@ -811,7 +847,10 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
   const int64_t ntl = (tile_end - tile_begin + tile_stride - 1) / tile_stride;
   const int js = choose_js(ntl);
   cull_set_dir(&win, dp);
-  rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, js, S, st);
+  // count-only sweeps without a mask: whole work items inside one class are counted in bulk
+  const bool bulk = stats == 0 && dp.model == SKG_DIR_NONE && getenv("SKG_BULK_OFF") == nullptr;
+  rc = launch_cull(coords, n, dim, win, tile_begin, tile_end, tile_stride, js, S, st,
+                   bulk ? &tab : nullptr, bulk ? reinterpret_cast<unsigned long long*>(count) : nullptr);
   if (rc) return rc;
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
   HistPartial* partial = reinterpret_cast<HistPartial*>(S.tail);
@@ -824,7 +863,7 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
                win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks, mv, S.bbox8};
   // register lag windows: 2-D isotropic sweeps over scalar values with an estimator sum
   const bool win_off = getenv("SKG_WIN_OFF") != nullptr;  // developer switch: first kernel only
-  if (!win_off && dim == 2 && dp.model == SKG_DIR_NONE && !use_mv && stats >= 1 && stats <= 3) {
+  if (!win_off && dim == 2 && dp.model == SKG_DIR_NONE && !use_mv && stats >= 0 && stats <= 3) {
     L.smem = hist_win_smem_bytes(n_lags, stats);
     if (L.smem <= 160 * 1024) {
       rc = dispatch_hist_win(tab.emax, stats, L);

@@ -806,7 +806,8 @@ int64_t sweep_head_bytes(int64_t n);
 int carve_scratch(void* scratch, int64_t scratch_bytes, int64_t n, int64_t need_tail, SweepScratch* out);
 int choose_js(int64_t tiles);
 int launch_cull(const double* coords, int64_t n, int dim, const CullWindows& win, int64_t t0,
-                int64_t t1, int64_t stride, int js, const SweepScratch& S, cudaStream_t st);
+                int64_t t1, int64_t stride, int js, const SweepScratch& S, cudaStream_t st,
+                const BinTable* bulk_tab = nullptr, unsigned long long* bulk_count = nullptr);
 
 // dir: 0 none, 1 mask with guard-band pairs excluded, 2 literal mask on the device
 int dispatch_hist(bool priv, int emax, int dim, int dir, int stats, const HistLaunch& L);   // pair_kernels.cu

@@ -25,7 +25,7 @@ namespace skg {
 // ------------------------------------------------------------ group size ---
 //
 // Mean diagonal of the boxes of 8/16/32 consecutive points against the mean lag-class width:
-// the largest group whose boxes usually fit a 3-class window wins (0 = windows off).
+// the largest group whose boxes usually fit a 2- or 3-class window wins (0 = windows off).
 __global__ void __launch_bounds__(256)
 win_plan_kernel(const double* __restrict__ bbox8, int64_t ngroups8, double last_edge_sq, int nb,
                 int force_g, unsigned long long* __restrict__ counters) {
@@ -72,11 +72,17 @@ win_plan_kernel(const double* __restrict__ bbox8, int64_t ngroups8, double last_
     } else if (m > 0 && nb >= 2 && last_edge_sq > 0.0 && last_edge_sq < 1e300) {
       const double width = sqrt(last_edge_sq) / nb;  // mean lag-class width
       a /= m; b /= m; c /= m;
-      if (c <= 1.1 * width) G = 32;
-      else if (b <= 1.1 * width) G = 16;
-      else if (a <= 1.3 * width) G = 8;
+      // measured (B200, uniform points, 25 even lags up to the median): 32-point groups win up to a
+      // box-diagonal / class-width ratio of ~1.6, 16-point groups up to ~2.2 (8-point groups never
+      // pay for their set-up); beyond that the per-pair path is faster
+      if (c <= 1.6 * width) G = 32;
+      else if (b <= 2.2 * width) G = 16;
     }
     counters[4] = (unsigned long long)G;
+    // for inspection (tools/win_bench.py): mean box diagonals of 16 / 32 points, mean class width
+    counters[5] = (unsigned long long)__double_as_longlong(m > 0 ? (force_g >= 0 ? b / m : b) : 0.0);
+    counters[6] = (unsigned long long)__double_as_longlong(m > 0 ? (force_g >= 0 ? c / m : c) : 0.0);
+    counters[7] = (unsigned long long)__double_as_longlong(nb > 0 ? sqrt(last_edge_sq) / nb : 0.0);
   }
 }
 
@@ -88,11 +94,22 @@ win_plan_kernel(const double* __restrict__ bbox8, int64_t ngroups8, double last_
 constexpr int WB = SKG_WIN_THREADS;  // threads per CTA
 constexpr int WR = TILE / WB;        // "i" points per thread
 constexpr int WIN_MIN_CTAS = WB == 64 ? 6 : 4;  // register cap: 168 / 128 per thread
+#ifndef SKG_WIN_UNROLL2
+#define SKG_WIN_UNROLL2 (SKG_WIN_THREADS == 64 ? 2 : 4)
+#endif
+constexpr int WIN_UNROLL2 = SKG_WIN_UNROLL2;  // j points in flight per thread in the 2-class loop
 
 
 template <int STATS>
 __device__ __forceinline__ void flush_row(unsigned saddr, unsigned caddr, double sq, double rt, unsigned cnt) {
-  if (STATS == 3) {
+  if (STATS == 0) {
+    asm volatile(
+        "{\n\t.reg .b32 c;\n\t"
+        "ld.shared.u32 c, [%0];\n\t"
+        "add.u32 c, c, %1;\n\t"
+        "st.shared.u32 [%0], c;\n\t}"
+        :: "r"(caddr), "r"(cnt));
+  } else if (STATS == 3) {
     asm volatile(
         "{\n\t.reg .b64 tb, rb;\n\t.reg .f64 t, u;\n\t.reg .b32 c;\n\t"
         "ld.shared.v2.b64 {tb, rb}, [%0];\n\t"
@@ -223,14 +240,14 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
       const bool v = i < n;
       xi[r] = v ? X[i] : qnan;
       yi[r] = v ? Y[i] : qnan;
-      zi[r] = v ? values[i] : 0.0;
+      zi[r] = (STATS != 0 && v) ? values[i] : 0.0;
     }
     __syncthreads();  // every read of the previous j chunk is done
     for (int k = tid; k < jcount + 2; k += WB) {  // two NaN entries pad the pipeline tail
       const int64_t j = (int64_t)J * TILE + jbeg + k;
       const bool v = k < jcount;
       sXY[k] = make_double2(v ? X[j] : qnan, v ? Y[j] : qnan);
-      sZ[k] = v ? values[j] : 0.0;
+      sZ[k] = (STATS != 0 && v) ? values[j] : 0.0;
     }
     if (G) {
       const int per = G >> 3;  // 8-point boxes per group
@@ -299,12 +316,12 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
     for (int g0 = 0; g0 < jcount; g0 += Gs) {
       unsigned gb[WR];
       double T1[WR], T2[WR];
-      bool all2 = false, all3 = false;
+      bool all1 = false, all2 = false, all3 = false;
       if (G) {
         const int gi = g0 >> gshift;
         const double2 blo = *reinterpret_cast<const double2*>(&sGB[gi][0]);
         const double2 bhi = *reinterpret_cast<const double2*>(&sGB[gi][2]);
-        bool fit2 = true, fit3 = true, dead = true;
+        bool fit1 = true, fit2 = true, fit3 = true, dead = true;
 #pragma unroll
         for (int r = 0; r < WR; ++r) {
           double smin, smax;
@@ -314,12 +331,14 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
           T1[r] = *reinterpret_cast<const double*>(thrBytes + g8);
           T2[r] = *reinterpret_cast<const double*>(thrBytes + g8 + 8);
           const double T3 = *reinterpret_cast<const double*>(thrBytes + g8 + 16);
+          fit1 &= smax < T1[r];   // the whole group in the point's own class
           fit2 &= smax < T2[r];   // NaN (flagged box, padded point): no window fits
           fit3 &= smax < T3;
           dead &= smin >= last_thr;
         }
         if (__all_sync(0xffffffffu, dead)) { SKG_DBG(0); continue; }  // the whole group lies beyond the last edge
-        all2 = __all_sync(0xffffffffu, fit2);
+        all1 = __all_sync(0xffffffffu, fit1);
+        all2 = all1 || __all_sync(0xffffffffu, fit2);
         all3 = all2 || __all_sync(0xffffffffu, fit3);
       }
       if (!all3) {
@@ -328,6 +347,28 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
         continue;
       }
       SKG_DBG(all2 ? 1 : 2);
+      if (all1) {
+        // one class for every pair of the group: no distance is evaluated at all
+        double q[WR], rs[WR];
+#pragma unroll
+        for (int r = 0; r < WR; ++r) q[r] = rs[r] = 0.0;
+        if (STATS != 0) {
+#pragma unroll 4
+          for (int jj = g0; jj < g0 + G; ++jj) {
+            const double zj = sZ[jj];
+#pragma unroll
+            for (int r = 0; r < WR; ++r) {
+              const double dz = zi[r] - zj;
+              if (STATS & SKG_STAT_SUM_SQ) q[r] = fma(dz, dz, q[r]);
+              if (STATS & SKG_STAT_SUM_SQRT) rs[r] += sqrt(fabs(dz));
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < WR; ++r)
+          flush_row<STATS>(aSum + gb[r] * SROW, aCnt + gb[r] * CROW, q[r], rs[r], (unsigned)G);
+        continue;
+      }
       // cumulative sums: A0 over all pairs of the group, A1 over s >= T1, A2 over s >= T2
       double q0[WR], q1[WR], q2[WR], r0[WR], r1[WR], r2[WR];
       unsigned c1[WR], c2[WR];
@@ -337,7 +378,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
         c1[r] = c2[r] = 0u;
       }
       if (all2) {
-#pragma unroll 2
+#pragma unroll WIN_UNROLL2
         for (int jj = g0; jj < g0 + G; ++jj) {
           const double2 pj = sXY[jj];
           const double zj = sZ[jj];
@@ -347,6 +388,10 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
             const double dy = yi[r] - pj.y;
             const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             const double dz = zi[r] - zj;
+            if (STATS == 0) {
+              asm("{\n\t.reg .pred p;\n\tsetp.ge.f64 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                  : "+r"(c1[r]) : "d"(s), "d"(T1[r]));
+            }
             if (STATS & SKG_STAT_SUM_SQ) {
               q0[r] = fma(dz, dz, q0[r]);
               asm("{\n\t.reg .pred p;\n\tsetp.ge.f64 p, %3, %4;\n\t"
@@ -378,6 +423,11 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
             const double dy = yi[r] - pj.y;
             const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             const double dz = zi[r] - zj;
+            if (STATS == 0) {
+              asm("{\n\t.reg .pred p, q;\n\tsetp.ge.f64 p, %2, %3;\n\tsetp.ge.f64 q, %2, %4;\n\t"
+                  "@p add.u32 %0, %0, 1;\n\t@q add.u32 %1, %1, 1;\n\t}"
+                  : "+r"(c1[r]), "+r"(c2[r]) : "d"(s), "d"(T1[r]), "d"(T2[r]));
+            }
             if (STATS & SKG_STAT_SUM_SQ) {
               q0[r] = fma(dz, dz, q0[r]);
               asm("{\n\t.reg .pred p, q;\n\tsetp.ge.f64 p, %5, %6;\n\tsetp.ge.f64 q, %5, %7;\n\t"
@@ -452,7 +502,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
 // ------------------------------------------------------------------ host ---
 
 size_t hist_win_smem_bytes(int nb, int stats) {
-  const int sumb = stats == 3 ? 16 : 8;
+  const int sumb = stats == 3 ? 16 : (stats == 0 ? 0 : 8);
   return ((size_t)(nb + 3) * WB * (sumb + 4) + 15) & ~(size_t)15;
 }
 
@@ -479,7 +529,7 @@ static int launch_hist_win_t(const HistLaunch& L) {
   return 0;
 }
 
-// 2-D, no directional mask, scalar values, stats in {1, 2, 3}.  The group size is planned on
+// 2-D, no directional mask, scalar values, stats in {0 (counts only), 1, 2, 3}.  The group size is planned on
 // the device from the boxes the culling prelude just wrote (no host round trip).
 int dispatch_hist_win(int emax, int stats, const HistLaunch& L) {
   int force_g = -1;
@@ -494,10 +544,12 @@ int dispatch_hist_win(int emax, int stats, const HistLaunch& L) {
                                        const_cast<unsigned long long*>(L.list_count));
   SKG_CUDA(cudaGetLastError());
   if (emax <= 1) {
+    if (stats == 0) return launch_hist_win_t<0, 1>(L);
     if (stats == 1) return launch_hist_win_t<1, 1>(L);
     if (stats == 2) return launch_hist_win_t<2, 1>(L);
     return launch_hist_win_t<3, 1>(L);
   }
+  if (stats == 0) return launch_hist_win_t<0, 0>(L);
   if (stats == 1) return launch_hist_win_t<1, 0>(L);
   if (stats == 2) return launch_hist_win_t<2, 0>(L);
   return launch_hist_win_t<3, 0>(L);

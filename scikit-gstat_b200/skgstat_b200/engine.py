@@ -73,6 +73,26 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy()
 
 
+import contextlib
+import os as _os
+import time as _time
+
+_DEBUG_TIMES = bool(_os.environ.get("SKG_SELECT_DEBUG"))
+
+
+@contextlib.contextmanager
+def _phase(label):
+    """Developer timing of one host-visible phase (SKG_SELECT_DEBUG=1); a no-op otherwise."""
+    if not _DEBUG_TIMES:
+        yield
+        return
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    yield
+    torch.cuda.synchronize()
+    print("   [phase] %-28s %.3f ms" % (label, (_time.perf_counter() - t0) * 1e3), flush=True)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -162,6 +182,7 @@ class PairEngine:
         self.pair_filter = None  # (exclusive upper bound of s as bits, drop s == 0): sparse max_dist spaces
         self.max_dist = None
         self._buffers = {}
+        self._sub_engine = None
         self._amb_cache = {}
         self.n_ambiguous = 0
         self.launches = 0  # kernels of this library enqueued (bench bookkeeping)
@@ -546,6 +567,14 @@ class PairEngine:
             return k, g * n_buckets + b
 
         def run_hist(lo, hi, sc):
+            with _phase("hist sweep (%d x %d)" % (nseg, n_buckets)):
+                return run_hist_(lo, hi, sc)
+
+        def run_gather(lo, hi, sc, bitmap, cap, want=None):
+            with _phase("gather sweep (cap %d)" % cap):
+                return run_gather_(lo, hi, sc, bitmap, cap, want)
+
+        def run_hist_(lo, hi, sc):
             hist = self._buffer("select_hist", nseg * n_buckets, torch.int64).zero_()
             mx = self._buffer("select_max", 1, torch.int64).zero_()
             lo = np.ascontiguousarray(lo, dtype=np.uint64)
@@ -572,7 +601,7 @@ class PairEngine:
                 collect_max.append(int(mx.item()))
             return to_host(hist)
 
-        def run_gather(lo, hi, sc, bitmap, cap, want=None):
+        def run_gather_(lo, hi, sc, bitmap, cap, want=None):
             """want = [(slot, [ranks relative to the slot's keys])]: the order statistics are
             picked on the device (sort of the gathered keys, one small copy back) and
             {slot: (count, {rank: key})} is returned instead of the raw candidates."""
@@ -694,6 +723,85 @@ class PairEngine:
         D.allreduce_sum_(cnt, self.group)
         return self._unmap(to_host(cnt).astype(np.int64), fsrc)
 
+    SUBSAMPLE_SELECT_MIN_PAIRS = 10 ** 8   # below this the 4096-cell sweep is cheap enough
+    SUBSAMPLE_POINTS = 8192
+    _select_mode = "auto"                  # "cells": always the log-cell sweep (tests)
+
+    def _subsample_engine(self):
+        """The same fixed-seed sub-sample of the points on every rank (no process group: each
+        rank repeats the small problem, so all ranks derive identical windows)."""
+        if self._sub_engine is None:
+            m = min(self.n, self.SUBSAMPLE_POINTS)
+            idx = np.sort(np.random.default_rng(777).choice(self.n, size=m, replace=False))
+            self._sub_engine = PairEngine(self._orig_coords[idx], None, device=self.device)
+        return self._sub_engine
+
+    def _window_cell_counts(self, rank_fn, hi_bits: int, limit):
+        """Cells of squared distance (upper bounds as bit patterns, exact pair counts) that are
+        narrow around every wanted rank - the input sq_order_stats gathers from - found WITHOUT
+        a sweep over all pairs: (1) the wanted quantiles of a fixed-seed sub-sample give a window
+        per rank; (2) exact counts per cell come from the count-only fused pass, in which every
+        work item / point group whose box lies inside one cell is counted in bulk (rows x columns),
+        so only the pairs near a cell boundary are evaluated; (3) cells still too crowded to gather
+        are subdivided and counted again.  A window that misses its rank just leaves a wide cell,
+        which step (3) refines: the result is exact either way."""
+        sub = self._subsample_engine()
+        m = float(sub.n)
+        state = {}
+
+        def sub_ranks(t):
+            # ranks of the window ends in the sub-sample: the wanted quantile -/+ 3 sigma of the
+            # empirical pair-distance distribution of m points (a miss only costs a refinement)
+            state["t"] = t
+            state["lo"], state["hi"] = [], []
+            if t < 1000:
+                return []
+            for r in sorted(set(int(r) for r in rank_fn(t))):
+                f = (r + 0.5) / t
+                h = 3.0 * np.sqrt(max(f * (1.0 - f), 1.0 / m) / m) + 4.0 / m
+                state["lo"].append(max(0, int(np.floor((f - h) * t))))
+                state["hi"].append(min(t - 1, int(np.ceil((f + h) * t))))
+            return sorted(set(state["lo"] + state["hi"]))
+
+        with _phase("sub-sample select"):
+            vals, st = sub.sq_order_stats(sub_ranks, limit=limit)
+        lo_r, hi_r = state["lo"], state["hi"]
+        if not lo_r:
+            return None
+        self.launches += sub.launches
+        sub.launches = 0
+        windows = []
+        for a, b in zip(lo_r, hi_r):
+            wl = 0 if a == 0 else to_bits(vals[a])
+            wh = hi_bits if b >= st - 1 else min(hi_bits, to_bits(vals[b]) + 1)
+            if wh > wl:
+                windows.append([wl, wh])
+        windows.sort()
+        merged = []
+        for w in windows:
+            if merged and w[0] <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], w[1])
+            else:
+                merged.append(w)
+        if not merged or len(merged) > 60:
+            return None
+        # cells: [0, w0.lo) | w0 | [w0.hi, w1.lo) | w1 | ... | [wK.hi, hi_bits).  Few, wide classes: the
+        # count-only fused pass handles them with bulk counts and register windows; the fine
+        # resolution inside the wanted windows comes from the histogram / gather passes, which only
+        # look at the tiles those windows touch
+        bounds, pos = [], 0
+        for wl, wh in merged:
+            if wl > pos:
+                bounds.append(wl)
+            bounds.append(wh)
+            pos = wh
+        if pos < hi_bits:
+            bounds.append(hi_bits)
+        thr = np.array(sorted(set(bounds)), dtype=np.uint64)
+        with _phase("count sweep (%d classes)" % thr.size):
+            counts = self.hist_counts(thr)
+        return thr, counts
+
     def sq_order_stats(self, rank_fn, dirp=None, limit: Optional[float] = None):
         """Exact order statistics of the squared distances s of all (mask-passing)
         pairs with fl(sqrt(s)) <= limit.  rank_fn(total) -> 0-based ranks.
@@ -712,7 +820,11 @@ class PairEngine:
         if self.pair_filter is not None:          # sparse space: 0 < d <= max_dist only
             hi_bits = min(hi_bits, self.pair_filter[0])
             zero_lo = 1 if self.pair_filter[1] else 0
-        thr, counts = self.sq_cell_counts(dirp, zero_lo, hi_bits)
+        cells = None
+        if (dirp is None and self.pair_filter is None and self.dim == 2
+                and self.n_pairs >= self.SUBSAMPLE_SELECT_MIN_PAIRS and self._select_mode != "cells"):
+            cells = self._window_cell_counts(rank_fn, hi_bits, limit)
+        thr, counts = cells if cells is not None else self.sq_cell_counts(dirp, zero_lo, hi_bits)
         total = int(counts.sum())
         ranks = sorted(set(int(r) for r in rank_fn(total)))
         for r in ranks:

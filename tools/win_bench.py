@@ -35,6 +35,8 @@ def kernel_ms(eng, thr, stats, reps=5):
             ts.append(e0.elapsed_time(e1))
     ctr = scratch[:128].view(torch.int64).cpu().numpy()
     g = int(ctr[4])
+    dd = ctr[5:8].view(np.float64)
+    print("      plan: diag16 %.3f diag32 %.3f width %.3f -> ratios %.2f %.2f" % (dd[0], dd[1], dd[2], dd[0] / dd[2], dd[1] / dd[2]))
     if ctr[8:14].any():   # debug build: warp-groups per path (dead, W=2, W=3, per-pair, diagonal items, culled items)
         print("      paths: dead %d  W2 %d  W3 %d  per-pair %d  diag items %d  culled warp-items %d  (list %d of %d)"
               % (ctr[8], ctr[9], ctr[10], ctr[11], ctr[12], ctr[13], ctr[0], ctr[3]))
