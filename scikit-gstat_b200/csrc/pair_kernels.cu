@@ -780,7 +780,7 @@ static int select_common(bool gather, const double* coords, const double* values
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
   SelectLaunch L{coords, values, n, &tab, &dp, &host_seg, n_buckets, hist, max_bits, bitmap,
                  cand_key, cand_slot, cand_count, capacity, ntiles, S.list, S.counters, S.bbox,
-                 S.bbox32, wlo, whi, js, st, mv};
+                 S.bbox32, wlo, whi, js, st, mv, getenv("SKG_GROUP_CULL_OFF") ? nullptr : S.bbox8};
   rc = use_mv ? dispatch_select_mv(gather, dim, use_dir, L)
               : dispatch_select(gather, dim, use_dir, n_lags > 0, key_kind, L);
   return rc;

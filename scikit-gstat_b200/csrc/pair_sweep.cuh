@@ -144,6 +144,7 @@ __device__ __forceinline__ void chunk_box(const double* __restrict__ bbox32, int
 // hoist the next pairs' loads and fp64 math above them.
 
 constexpr int HB_THREADS = 64;  // threads per CTA of the fused / select sweeps (= HB)
+constexpr int SEL_GROUP = 16;   // j points per group of the select passes' group-level culling
 
 struct DzTable {  // per-lag |dz| thresholds of the below-count mode (STATS == 4)
   double lo[THR_MAX];
@@ -286,7 +287,11 @@ __device__ __forceinline__ int lag_of(uint64_t sb, const uint64_t* sThr, const u
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) g += (s >= dThr[g]) ? 1 : 0;
   } else {
-    for (int e = 0; e < emax; ++e) g += (s >= dThr[g]) ? 1 : 0;
+    // many thresholds may share one cell (clustered edges): stop at the first one above s
+    for (int e = 0; e < emax; ++e) {
+      if (!(s >= dThr[g])) break;
+      ++g;
+    }
   }
   return g;
 }
@@ -308,8 +313,11 @@ __device__ __forceinline__ unsigned lag_off8(uint64_t sb, const uint64_t* sThr,
     for (int e = 0; e < EMAX; ++e)
       g8 += (s >= *reinterpret_cast<const double*>(thrBytes + g8)) ? 8u : 0u;
   } else {
-    for (int e = 0; e < emax; ++e)
-      g8 += (s >= *reinterpret_cast<const double*>(thrBytes + g8)) ? 8u : 0u;
+    // many thresholds may share one cell (clustered edges): stop at the first one above s
+    for (int e = 0; e < emax; ++e) {
+      if (!(s >= *reinterpret_cast<const double*>(thrBytes + g8))) break;
+      g8 += 8u;
+    }
   }
   return g8;
 }
@@ -554,13 +562,14 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
                    long long capacity, const unsigned int* __restrict__ tile_list,
                    const unsigned long long* __restrict__ tile_count,
                    const double* __restrict__ bbox, const double* __restrict__ bbox32, double wlo,
-                   double whi, int js, const MvSpec mv) {
+                   double whi, int js, const MvSpec mv, const double* __restrict__ bbox8) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
   __shared__ uint64_t sThr[THR_MAX];
   __shared__ uint8_t sLut[LUT_MAX];
   __shared__ SegTable sSeg;
+  __shared__ double sGB[DIM == 2 ? TILE / SEL_GROUP : 1][4];  // boxes of the chunk's 16-point j groups
   extern __shared__ __align__(16) unsigned char mv_raw[];  // VM: value columns of both tiles
   double* mvI = reinterpret_cast<double*>(mv_raw);
   double* mvJ = mvI + (VM ? mv.nv * TILE : 0);
@@ -637,10 +646,72 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
         }
       }
     }
+    const bool grouped = DIM == 2 && bbox8 != nullptr && I != J;  // group-level culling (below)
+    if (grouped) {
+      for (int g = tid; g < jchunk / SEL_GROUP; g += HB) {
+        const int64_t b8 = ((int64_t)J * TILE + jbeg) / 8 + (int64_t)g * (SEL_GROUP / 8);
+        double lx = bbox8[b8 * 4], ly = bbox8[b8 * 4 + 1], hx = bbox8[b8 * 4 + 2], hy = bbox8[b8 * 4 + 3];
+        bool bad = !(lx == lx);
+#pragma unroll
+        for (int u = 1; u < SEL_GROUP / 8; ++u) {
+          const double l2 = bbox8[(b8 + u) * 4];
+          bad |= !(l2 == l2);
+          lx = fmin(lx, l2);
+          ly = fmin(ly, bbox8[(b8 + u) * 4 + 1]);
+          hx = fmax(hx, bbox8[(b8 + u) * 4 + 2]);
+          hy = fmax(hy, bbox8[(b8 + u) * 4 + 3]);
+        }
+        if (bad) lx = ly = hx = hy = qnan;  // NaN / missing point: the group is always swept
+        sGB[DIM == 2 ? g : 0][0] = lx; sGB[DIM == 2 ? g : 0][1] = ly;
+        sGB[DIM == 2 ? g : 0][2] = hx; sGB[DIM == 2 ? g : 0][3] = hy;
+      }
+    }
     __syncthreads();
     if (jcount == 0 || !wact) continue;
 
-    auto body = [&](auto diag_tag) {
+    // Group-level culling: can any pair of (this warp's points) x (16 consecutive j points) fall
+    // into a window?  [smin, smax] = point-to-box range of the squared distance, formed with the
+    // pair arithmetic (rigorous by monotone rounding).  Distance keys: some window must meet the
+    // range; |dz| keys: some lag class met by the range must have a window at all.
+    auto group_needed = [&](int g0) -> bool {
+      if (!grouped) return true;
+      if (!SEG && !GATHER && max_bits) return true;  // the running maximum looks at every pair
+      const int gi = g0 / SEL_GROUP;
+      const double lox = sGB[DIM == 2 ? gi : 0][0], loy = sGB[DIM == 2 ? gi : 0][1];
+      const double hix = sGB[DIM == 2 ? gi : 0][2], hiy = sGB[DIM == 2 ? gi : 0][3];
+      bool need = false;
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        const double ax = xi[r] - lox, bx = xi[r] - hix, ay = yi[r] - loy, by = yi[r] - hiy;
+        const double ax2 = __dmul_rn(ax, ax), bx2 = __dmul_rn(bx, bx);
+        const double ay2 = __dmul_rn(ay, ay), by2 = __dmul_rn(by, by);
+        const bool gx = ax2 > bx2, gy = ay2 > by2;
+        const double fx = gx ? ax2 : bx2, fy = gy ? ay2 : by2;
+        double nx = gx ? bx2 : ax2, ny = gy ? by2 : ay2;
+        if ((__double2hiint(ax) ^ __double2hiint(bx)) < 0) nx = 0.0;
+        if ((__double2hiint(ay) ^ __double2hiint(by)) < 0) ny = 0.0;
+        const double smin = __dadd_rn(nx, ny), smax = __dadd_rn(fx, fy);
+        if (!(smax == smax) || !(smin == smin)) { need = true; continue; }  // flagged box / padded point
+        const uint64_t bmin = (uint64_t)__double_as_longlong(smin), bmax = (uint64_t)__double_as_longlong(smax);
+        if (!SEG) {
+          if (KEY == SKG_KEY_SQDIST) need |= (bmin < sSeg.hi_bits[0]) & (bmax >= sSeg.lo_bits[0]);
+          else need |= sSeg.hi_bits[0] > sSeg.lo_bits[0];
+        } else {
+          const int c0 = lag_of<EMAX>(bmin, sThr, lutb, shift, klo, khi, emax);
+          int c1 = lag_of<EMAX>(bmax, sThr, lutb, shift, klo, khi, emax);
+          c1 = c1 < nb - 1 ? c1 : nb - 1;
+          if (c1 - c0 > 3) { need = true; continue; }
+          for (int c = c0; c <= c1; ++c) {
+            const uint64_t wl = sSeg.lo_bits[c], wh = sSeg.hi_bits[c];
+            if (KEY == SKG_KEY_SQDIST) need |= (wh > wl) & (bmin < wh) & (bmax >= wl);
+            else need |= wh > wl;
+          }
+        }
+      }
+      return __any_sync(0xffffffffu, need);
+    };
+
+    auto body = [&](auto diag_tag, int j0, int j1) {
       constexpr bool DIAG = decltype(diag_tag)::value;
       auto front = [&](int jj, int (&g)[HR], double (&key)[HR]) {
         const double2 pj = sXY[jj];
@@ -703,20 +774,31 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
       };
       int gA[HR], gB[HR];
       double kA[HR], kB[HR];
-      front(0, gA, kA);
-      int jj = 1;
-      for (; jj + 1 <= jcount; jj += 2) {
+      front(j0, gA, kA);
+      int jj = j0 + 1;
+      for (; jj + 1 <= j1; jj += 2) {  // the entry at j1 is a later point or NaN padding: never used
         front(jj, gB, kB);
         accumulate(gA, kA);
         front(jj + 1, gA, kA);
         accumulate(gB, kB);
       }
-      if (jj <= jcount) {
+      if (jj <= j1) {
         front(jj, gB, kB);
         accumulate(gA, kA);
       }
     };
-    if (I == J) body(std::true_type{}); else body(std::false_type{});
+    if (I == J) {
+      body(std::true_type{}, 0, jcount);
+    } else {
+      // consecutive needed groups are swept as one range (keeps the software pipeline long)
+      int run0 = -1;
+      for (int g0 = 0;; g0 += SEL_GROUP) {
+        const bool need = g0 < jcount && group_needed(g0);
+        if (need && run0 < 0) run0 = g0;
+        if (!need && run0 >= 0) { body(std::false_type{}, run0, min(g0, jcount)); run0 = -1; }
+        if (g0 >= jcount) break;
+      }
+    }
   }
   if (!SEG && !GATHER && max_bits) {
     unsigned long long m = local_max;
@@ -780,6 +862,7 @@ struct SelectLaunch {
   int64_t ntiles; const unsigned int* list; const unsigned long long* list_count;
   const double* bbox; const double* bbox32; double wlo, whi; int js; cudaStream_t st;
   MvSpec mv;
+  const double* bbox8;
 };
 
 template <int DIM, int DIR, bool SEG, int KEY, bool GATHER, int EMAX, bool VM>
@@ -795,7 +878,7 @@ static int launch_select(const SelectLaunch& L) {
       L.coords, L.values, L.n, *L.tab, *L.dp, *L.seg, (long long)L.nbuckets,
       reinterpret_cast<unsigned long long*>(L.hist), reinterpret_cast<unsigned long long*>(L.max_bits),
       L.bitmap, L.cand_key, L.cand_slot, reinterpret_cast<unsigned long long*>(L.cand_count),
-      (long long)L.capacity, L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi, L.js, L.mv);
+      (long long)L.capacity, L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi, L.js, L.mv, L.bbox8);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -723,8 +723,10 @@ class PairEngine:
         D.allreduce_sum_(cnt, self.group)
         return self._unmap(to_host(cnt).astype(np.int64), fsrc)
 
-    SUBSAMPLE_SELECT_MIN_PAIRS = 10 ** 8   # below this the 4096-cell sweep is cheap enough
+    SUBSAMPLE_SELECT_MIN_PAIRS = 10 ** 9   # below this the 4096-cell sweep is cheap enough
     SUBSAMPLE_POINTS = 8192
+    REFINE_CELLS = 16                      # narrow cells counted around an interpolated rank
+    REFINE_CELL_KEYS = 1 << 20             # keys aimed for per refinement cell
     _select_mode = "auto"                  # "cells": always the log-cell sweep (tests)
 
     def _subsample_engine(self):
@@ -783,7 +785,9 @@ class PairEngine:
                 merged[-1][1] = max(merged[-1][1], w[1])
             else:
                 merged.append(w)
-        if not merged or len(merged) > 60:
+        if not merged or len(merged) > 2:
+            # many quantiles at once (uniform-count bins): the windows of an 8192-point sample would
+            # together hold a third of all pairs - the log-cell sweep is the better first pass there
             return None
         # cells: [0, w0.lo) | w0 | [w0.hi, w1.lo) | w1 | ... | [wK.hi, hi_bits).  Few, wide classes: the
         # count-only fused pass handles them with bulk counts and register windows; the fine
@@ -800,7 +804,54 @@ class PairEngine:
         thr = np.array(sorted(set(bounds)), dtype=np.uint64)
         with _phase("count sweep (%d classes)" % thr.size):
             counts = self.hist_counts(thr)
-        return thr, counts
+        # second level: inside a window the distribution of s is smooth, so linear interpolation of
+        # the exact counts at its ends predicts a wanted rank to ~1 % of the window's keys; a band
+        # of REFINE_CELLS narrow cells around the prediction is counted exactly (again in bulk
+        # outside the band) and the cell that holds the rank is small enough to gather directly
+        total = int(counts.sum())
+        ranks = sorted(set(int(r) for r in rank_fn(total)))
+        if not ranks:
+            return thr, counts
+        cum = np.cumsum(counts)
+        lows = np.concatenate((np.zeros(1, dtype=np.uint64), thr[:-1]))   # (a Python 0 would promote to float64)
+        bands = {}   # window class -> thresholds strictly inside it
+        for r in ranks:
+            c = int(np.searchsorted(cum, r, side="right"))
+            n_in = int(counts[c])
+            if n_in <= self.DIRECT_GATHER_LIMIT // 2:
+                continue
+            lo_v, hi_v = from_bits(int(lows[c])), from_bits(int(thr[c]) - 1)
+            if not (np.isfinite(lo_v) and np.isfinite(hi_v) and hi_v > lo_v):
+                continue
+            rel = (r - (int(cum[c - 1]) if c else 0) + 0.5) / n_in
+            frac_cell = min(0.25, self.REFINE_CELL_KEYS / n_in)       # mass of one refinement cell
+            half = self.REFINE_CELLS // 2
+            for k in range(-half, half + 1):
+                f = rel + k * frac_cell
+                if 0.0 < f < 1.0:
+                    t = to_bits(lo_v + (hi_v - lo_v) * f)
+                    if int(lows[c]) < t < int(thr[c]):
+                        bands.setdefault(c, set()).add(t)
+        if not bands:
+            return thr, counts
+        # one sweep per refined window over [window start, window end) only: the lag table then
+        # resolves the narrow cells (nothing beyond the window is swept, pairs below it are bulk)
+        out_thr, out_cnt = [], []
+        for c in range(thr.size):
+            if c not in bands:
+                out_thr.append(int(thr[c]))
+                out_cnt.append(int(counts[c]))
+                continue
+            inner = sorted(bands[c])
+            t2 = np.array(([int(lows[c])] if int(lows[c]) > 0 else []) + inner + [int(thr[c])], dtype=np.uint64)
+            with _phase("count sweep (%d classes, window)" % t2.size):
+                c2 = self.hist_counts(t2)
+            c2 = c2[1:] if int(lows[c]) > 0 else c2          # drop the class below the window
+            if int(c2.sum()) != int(counts[c]):
+                raise RuntimeError("window refinement count mismatch: %d != %d" % (int(c2.sum()), int(counts[c])))
+            out_thr += inner + [int(thr[c])]
+            out_cnt += [int(x) for x in c2]
+        return np.array(out_thr, dtype=np.uint64), np.array(out_cnt, dtype=np.int64)
 
     def sq_order_stats(self, rank_fn, dirp=None, limit: Optional[float] = None):
         """Exact order statistics of the squared distances s of all (mask-passing)

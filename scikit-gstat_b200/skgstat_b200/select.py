@@ -63,7 +63,11 @@ def exact_select(nseg: int, lo_bits: Sequence[int], hi_bits: Sequence[int], n_bu
             lo[g], hi[g] = w[0], w[1]
             sc[g] = _scale_for(w[0], w[1], n_buckets)
         hist = np.asarray(run_hist(lo, hi, sc)).reshape(nseg, n_buckets).astype(np.int64)
-        gather = []  # (g, bucket, base_in_window, count, ranks)
+        # runs to gather: (g, lo_bits, hi_bits, rank of the first key of the run, keys in the run, ranks).
+        # A run is the key range of one bucket (or of neighbouring wanted buckets of a segment): the
+        # gather pass gets exactly that range as the segment's window (one bucket, scale 0), so its
+        # tile culling works on the narrow range instead of the whole histogram window.
+        runs = []
         for g, w in enumerate(cur):
             if w is None:
                 continue
@@ -81,6 +85,7 @@ def exact_select(nseg: int, lo_bits: Sequence[int], hi_bits: Sequence[int], n_bu
             cum = np.cumsum(row)
             rel = np.asarray(ranks, dtype=np.int64) - w_base
             buckets = np.searchsorted(cum, rel, side="right")
+            seg_runs = []
             for b in np.unique(buckets):
                 b = int(b)
                 rs = [r for r, bb in zip(ranks, buckets) if bb == b]
@@ -91,50 +96,67 @@ def exact_select(nseg: int, lo_bits: Sequence[int], hi_bits: Sequence[int], n_bu
                         values[g][r] = from_bits(w_lo)
                     continue
                 single_bucket = sc[g] == 0.0
-                if cnt <= bucket_limit or single_bucket:
-                    gather.append((g, b, w_base + below, cnt, rs))
+                if single_bucket:
+                    nlo, nhi = w_lo, w_hi
                 else:
                     nlo = bucket_lower_bits(b, w_lo, w_hi, float(sc[g]), n_buckets)
                     nhi = bucket_lower_bits(b + 1, w_lo, w_hi, float(sc[g]), n_buckets) \
                         if b + 1 < n_buckets else w_hi
+                if cnt <= bucket_limit or single_bucket:
+                    prev = seg_runs[-1] if seg_runs else None
+                    if prev is not None and prev[2] == nlo and prev[4] + cnt <= bucket_limit:
+                        prev[2], prev[4] = nhi, prev[4] + cnt   # neighbouring bucket: one run
+                        prev[5].extend(rs)
+                    else:
+                        seg_runs.append([g, nlo, nhi, w_base + below, cnt, list(rs)])
+                else:
                     pending[g].append((nlo, nhi, w_base + below, rs))
+            runs.extend(seg_runs)
         first = False
-        # gather in batches that respect the capacity limit
-        while gather:
-            batch, cap = [], 0
-            while gather and (not batch or cap + gather[-1][3] <= gather_limit):
-                item = gather.pop()
-                batch.append(item)
-                cap += item[3]
+        # gather calls: at most one run per segment and call, total keys within the capacity limit
+        while runs:
+            batch, cap, used, rest = [], 0, set(), []
+            for run in runs:
+                if run[0] in used or (batch and cap + run[4] > gather_limit):
+                    rest.append(run)
+                else:
+                    batch.append(run)
+                    used.add(run[0])
+                    cap += run[4]
+            runs = rest
+            glo = np.zeros(nseg, dtype=np.uint64)
+            ghi = np.zeros(nseg, dtype=np.uint64)
+            gsc = np.zeros(nseg, dtype=np.float64)   # scale 0: every key of the window is bucket 0
             bitmap = np.zeros((nseg * n_buckets + 31) // 32, dtype=np.uint32)
-            for g, b, _, _, _ in batch:
-                slot = g * n_buckets + b
+            for g, nlo, nhi, _, _, _ in batch:
+                glo[g], ghi[g] = nlo, nhi
+                slot = g * n_buckets
                 bitmap[slot >> 5] |= np.uint32(1 << (slot & 31))
             if getattr(run_gather, "device_pick", False):
                 # the runner sorts the gathered keys where they are and returns only the wanted ranks
-                want = [(g * n_buckets + b, sorted(set(int(r - base) for r in rs)))
-                        for g, b, base, cnt, rs in batch]
-                picked = run_gather(lo, hi, sc, bitmap, cap, want)
-                for g, b, base, cnt, rs in batch:
-                    got, vals = picked[g * n_buckets + b]
+                want = [(g * n_buckets, sorted(set(int(r - base) for r in rs)))
+                        for g, _, _, base, cnt, rs in batch]
+                picked = run_gather(glo, ghi, gsc, bitmap, cap, want)
+                for g, _, _, base, cnt, rs in batch:
+                    got, vals = picked[g * n_buckets]
                     if got != cnt:
-                        raise RuntimeError("bucket (%d,%d): gathered %d, counted %d" % (g, b, got, cnt))
+                        raise RuntimeError("segment %d: gathered %d keys, counted %d" % (g, got, cnt))
                     for r in rs:
                         values[g][r] = vals[int(r - base)]
                 continue
-            keys, slots = run_gather(lo, hi, sc, bitmap, cap)
+            keys, slots = run_gather(glo, ghi, gsc, bitmap, cap)
             keys = np.asarray(keys, dtype=np.float64)
             slots = np.asarray(slots, dtype=np.int64)
             if keys.size != cap:
                 raise RuntimeError("gather returned %d keys, histogram promised %d" % (keys.size, cap))
             order = np.argsort(slots, kind="stable")
             keys, slots = keys[order], slots[order]
-            for g, b, base, cnt, rs in batch:
-                slot = g * n_buckets + b
+            for g, _, _, base, cnt, rs in batch:
+                slot = g * n_buckets
                 a = np.searchsorted(slots, slot, side="left")
                 z = np.searchsorted(slots, slot, side="right")
                 if z - a != cnt:
-                    raise RuntimeError("bucket (%d,%d): gathered %d, counted %d" % (g, b, z - a, cnt))
+                    raise RuntimeError("segment %d: gathered %d keys, counted %d" % (g, z - a, cnt))
                 idx = sorted(set(int(r - base) for r in rs))
                 vals = np.partition(keys[a:z], idx)   # exact order statistics, O(n)
                 for r in rs:
