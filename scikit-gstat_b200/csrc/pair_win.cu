@@ -360,7 +360,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
             for (int r = 0; r < WR; ++r) {
               const double dz = zi[r] - zj;
               if (STATS & SKG_STAT_SUM_SQ) q[r] = fma(dz, dz, q[r]);
-              if (STATS & SKG_STAT_SUM_SQRT) rs[r] += sqrt(fabs(dz));
+              if (STATS & SKG_STAT_SUM_SQRT) rs[r] += sqrt_abs(dz);
             }
           }
         }
@@ -399,7 +399,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
                   : "+d"(q1[r]), "+r"(c1[r]) : "d"(dz), "d"(s), "d"(T1[r]));
             }
             if (STATS & SKG_STAT_SUM_SQRT) {
-              const double rt = sqrt(fabs(dz));
+              const double rt = sqrt_abs(dz);
               r0[r] += rt;
               if (STATS & SKG_STAT_SUM_SQ) {
                 asm("{\n\t.reg .pred p;\n\tsetp.ge.f64 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
@@ -437,7 +437,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
                   : "d"(dz), "d"(s), "d"(T1[r]), "d"(T2[r]));
             }
             if (STATS & SKG_STAT_SUM_SQRT) {
-              const double rt = sqrt(fabs(dz));
+              const double rt = sqrt_abs(dz);
               r0[r] += rt;
               if (STATS & SKG_STAT_SUM_SQ) {
                 asm("{\n\t.reg .pred p, q;\n\tsetp.ge.f64 p, %3, %4;\n\tsetp.ge.f64 q, %3, %5;\n\t"

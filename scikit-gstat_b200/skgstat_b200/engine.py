@@ -730,8 +730,9 @@ class PairEngine:
     _select_mode = "auto"                  # "cells": always the log-cell sweep (tests)
 
     def _subsample_engine(self):
-        """The same fixed-seed sub-sample of the points on every rank (no process group: each
-        rank repeats the small problem, so all ranks derive identical windows)."""
+        """The same fixed-seed sub-sample of the points on every rank.  Like every engine it shards
+        its sweeps over the default process group when one is initialised; all ranks walk through
+        the same calls, so they derive identical windows."""
         if self._sub_engine is None:
             m = min(self.n, self.SUBSAMPLE_POINTS)
             idx = np.sort(np.random.default_rng(777).choice(self.n, size=m, replace=False))
