@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SKG_ABI_VERSION 4
+#define SKG_ABI_VERSION 5
 #define SKG_TILE 256            /* points per tile edge                          */
 #define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
 #define SKG_KRIGE_MAX_POINTS 64 /* max_points supported by the warp-per-target kernel */
@@ -179,6 +179,22 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
                   uint64_t* count, double* sum_sq, double* sum_sqrt,
                   void* scratch, int64_t scratch_bytes,
                   int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
+
+/* K3a - one sweep for the windowed Dowd median (estimators.py:131-178, np.nanmedian per lag class):
+ * per lag class the exact pair count, the count of pairs with |dz| below the class's window
+ * [dz_lo, dz_hi) (private counters, no atomics) AND the fine histogram of the |dz| inside the
+ * window (one L2 atomic for the few in-window pairs; bucket function as skg_pair_select_hist).
+ * Replaces a skg_pair_hist(SKG_STAT_COUNT_BELOW) sweep followed by a skg_pair_select_hist sweep.
+ *   dz_lo_bits/dz_hi_bits [host, n_lags] bit patterns of the window ends, dz_scale [host, n_lags]
+ *   count [dev, n_lags] += pairs;  below [dev, n_lags] (double) += pairs with |dz| < dz_lo
+ *   hist  [dev, n_lags*n_buckets] += in-window pairs per bucket
+ * Everything else (values, dir, thr_bits, scratch, tiles, culling, determinism) as skg_pair_hist. */
+int skg_pair_dz_windows(const double* coords, const double* values, int n_values, int value_mode,
+                        int64_t n, int dim, const double* dir, const uint64_t* thr_bits, int n_lags,
+                        const uint64_t* dz_lo_bits, const uint64_t* dz_hi_bits, const double* dz_scale,
+                        int64_t n_buckets, uint64_t* count, double* below, uint64_t* hist,
+                        void* scratch, int64_t scratch_bytes,
+                        int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
 
 /* K2b - batched fused pass: the estimator sums of n_vectors value vectors that share the
  * coordinates, in ceil(n_vectors/4) sweeps (4 vectors per sweep; distance, lag class and pair

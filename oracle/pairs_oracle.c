@@ -18,7 +18,7 @@
  *
  * The lag class is found on d = sqrt(s) against the edges themselves (binary search), NOT in
  * squared space: it is independent of the product's threshold trick and therefore checks it.
- * The mask uses libm acos/sin while the reference uses numpy's; pairs within 1e-9 of a decision
+ * The mask uses libm acos/sin while the reference uses numpy's; pairs within 1e-12 of a decision
  * boundary are counted in *n_guard so the caller can see whether that could matter (it is 0
  * for the generic float inputs of the golden cases).
  *
@@ -56,11 +56,11 @@ static inline int mask_pass(double dx, double dy, double d, const dir_t* p, int*
   if (a > PI) a = a - PI;
   if (a > PI / 2) a = PI - a;
   int in_tol = a <= p->half_tol;
-  if (fabs(a - p->half_tol) <= 1e-9) *near = 1;
+  if (fabs(a - p->half_tol) <= 1e-12) *near = 1;
   if (p->model == 2) return in_tol;
   double w = fabs(d * sin(t));
   int in_band = p->half_bw >= w;
-  if (fabs(p->half_bw - w) <= 1e-9 * (p->half_bw + 1.0)) *near = 1;
+  if (fabs(p->half_bw - w) <= 1e-12 * (p->half_bw + 1.0)) *near = 1;
   return in_tol && in_band;
 }
 

@@ -805,12 +805,13 @@ int64_t skg_pair_scratch_bytes(int64_t n, int n_lags) {
          (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
 }
 
-int skg_pair_hist(const double* coords, const double* values, int n_values, int value_mode,
-                  int64_t n, int dim, const double* dir,
-                  const uint64_t* thr_bits, int n_lags, int stats, const double* dz_lo,
-                  uint64_t* count, double* sum_sq, double* sum_sqrt, void* scratch,
-                  int64_t scratch_bytes, int64_t tile_begin, int64_t tile_end, int64_t tile_stride,
-                  void* stream) {
+static int pair_hist_impl(const double* coords, const double* values, int n_values, int value_mode,
+                          int64_t n, int dim, const double* dir,
+                          const uint64_t* thr_bits, int n_lags, int stats, const double* dz_lo,
+                          const double* dz_hi, const double* dz_scale, int64_t n_buckets, uint64_t* whist,
+                          uint64_t* count, double* sum_sq, double* sum_sqrt, void* scratch,
+                          int64_t scratch_bytes, int64_t tile_begin, int64_t tile_end, int64_t tile_stride,
+                          void* stream) {
   int rc = check_pair_args(coords, n, dim, tile_begin, tile_end, tile_stride);
   if (rc) return rc;
   const bool dist_mode = (value_mode & ~SKG_VALUE_SQUARE_FLAG) >= SKG_VALUE_DIST_S &&
@@ -858,9 +859,14 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
   DzTable dzt;
   std::memset(&dzt, 0, sizeof(dzt));
   if (stats == SKG_STAT_COUNT_BELOW)
-    for (int k = 0; k < n_lags; ++k) dzt.lo[k] = dz_lo[k];
+    for (int k = 0; k < n_lags; ++k) {
+      dzt.lo[k] = dz_lo[k];
+      dzt.hi[k] = whist ? dz_hi[k] : 0.0;
+      dzt.scale[k] = whist ? dz_scale[k] : 0.0;
+    }
   HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, S.bbox, S.bbox32,
-               win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks, mv, S.bbox8};
+               win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks, mv, S.bbox8,
+               reinterpret_cast<unsigned long long*>(whist), (long long)n_buckets};
   // register lag windows: 2-D isotropic sweeps over scalar values with an estimator sum
   const bool win_off = getenv("SKG_WIN_OFF") != nullptr;  // developer switch: first kernel only
   if (!win_off && dim == 2 && dp.model == SKG_DIR_NONE && !use_mv && stats >= 0 && stats <= 3) {
@@ -892,6 +898,39 @@ int skg_pair_hist(const double* coords, const double* values, int n_values, int 
       (stats != SKG_STAT_COUNT_BELOW && (stats & SKG_STAT_SUM_SQRT)) ? sum_sqrt : nullptr);
   SKG_CUDA(cudaGetLastError());
   return 0;
+}
+
+int skg_pair_hist(const double* coords, const double* values, int n_values, int value_mode,
+                  int64_t n, int dim, const double* dir,
+                  const uint64_t* thr_bits, int n_lags, int stats, const double* dz_lo,
+                  uint64_t* count, double* sum_sq, double* sum_sqrt, void* scratch,
+                  int64_t scratch_bytes, int64_t tile_begin, int64_t tile_end, int64_t tile_stride,
+                  void* stream) {
+  return pair_hist_impl(coords, values, n_values, value_mode, n, dim, dir, thr_bits, n_lags, stats, dz_lo,
+                        nullptr, nullptr, 0, nullptr, count, sum_sq, sum_sqrt, scratch, scratch_bytes,
+                        tile_begin, tile_end, tile_stride, stream);
+}
+
+int skg_pair_dz_windows(const double* coords, const double* values, int n_values, int value_mode,
+                        int64_t n, int dim, const double* dir, const uint64_t* thr_bits, int n_lags,
+                        const uint64_t* dz_lo_bits, const uint64_t* dz_hi_bits, const double* dz_scale,
+                        int64_t n_buckets, uint64_t* count, double* below, uint64_t* hist, void* scratch,
+                        int64_t scratch_bytes, int64_t tile_begin, int64_t tile_end, int64_t tile_stride,
+                        void* stream) {
+  if (!dz_lo_bits || !dz_hi_bits || !dz_scale || !hist || !below || n_buckets < 1 || n_lags < 1 ||
+      n_lags > SKG_MAX_LAGS) {
+    set_error("window arguments NULL, n_buckets < 1 or n_lags outside [1, %d]", SKG_MAX_LAGS);
+    return SKG_E_BADARG;
+  }
+  double lo[SKG_MAX_LAGS], hi[SKG_MAX_LAGS];
+  for (int k = 0; k < n_lags; ++k) {
+    std::memcpy(&lo[k], &dz_lo_bits[k], 8);
+    std::memcpy(&hi[k], &dz_hi_bits[k], 8);
+    if (dz_hi_bits[k] > INF_BITS) hi[k] = bits_to_double(INF_BITS);
+  }
+  return pair_hist_impl(coords, values, n_values, value_mode, n, dim, dir, thr_bits, n_lags,
+                        SKG_STAT_COUNT_BELOW, lo, hi, dz_scale, n_buckets, hist, count, below, nullptr,
+                        scratch, scratch_bytes, tile_begin, tile_end, tile_stride, stream);
 }
 
 int skg_pair_select_hist(const double* coords, const double* values, int n_values, int value_mode,

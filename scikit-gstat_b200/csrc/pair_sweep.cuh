@@ -146,8 +146,10 @@ __device__ __forceinline__ void chunk_box(const double* __restrict__ bbox32, int
 constexpr int HB_THREADS = 64;  // threads per CTA of the fused / select sweeps (= HB)
 constexpr int SEL_GROUP = 16;   // j points per group of the select passes' group-level culling
 
-struct DzTable {  // per-lag |dz| thresholds of the below-count mode (STATS == 4)
-  double lo[THR_MAX];
+struct DzTable {  // per-lag |dz| windows of the below-count mode (STATS == 4)
+  double lo[THR_MAX];     // pairs with |dz| < lo are counted "below"
+  double hi[THR_MAX];     // with a window histogram: lo <= |dz| < hi lands in a bucket
+  double scale[THR_MAX];  // bucket = min(B-1, trunc(fl(fl(|dz| - lo) * scale))), as the select passes
 };
 
 struct HistPartial {  // one per (CTA, lag class)
@@ -349,13 +351,16 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
                  HistPartial* __restrict__ partial, const unsigned int* __restrict__ tile_list,
                  const unsigned long long* __restrict__ tile_count,
                  const double* __restrict__ bbox, const double* __restrict__ bbox32, double wlo,
-                 double whi, const __grid_constant__ DzTable dzt, int js, const MvSpec mv) {
+                 double whi, const __grid_constant__ DzTable dzt, int js, const MvSpec mv,
+                 unsigned long long* __restrict__ whist, long long wbuckets) {
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
   __shared__ uint64_t sThr[THR_MAX];
   __shared__ uint16_t sLut[LUT_MAX];  // lut[cell] * 8
   __shared__ double sDzLo[STATS == 4 ? THR_MAX : 1];  // per-lag |dz| thresholds (below-count mode)
+  __shared__ double sDzHi[STATS == 4 ? THR_MAX : 1];
+  __shared__ double sDzSc[STATS == 4 ? THR_MAX : 1];
   extern __shared__ __align__(16) unsigned char acc_raw[];
 
   constexpr int REC = (STATS == 3) ? 32 : 16;              // shared records of the !PRIV path
@@ -368,7 +373,11 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
   for (int k = tid; k < THR_MAX; k += HB) sThr[k] = tab.thr[k];
   for (int k = tid; k < tab.ncell; k += HB) sLut[k] = (uint16_t)(tab.lut[k] * 8);
   if (STATS == 4) {
-    for (int k = tid; k < THR_MAX; k += HB) sDzLo[k] = k < nb ? dzt.lo[k] : 0.0;
+    for (int k = tid; k < THR_MAX; k += HB) {
+      sDzLo[k] = k < nb ? dzt.lo[k] : 0.0;
+      sDzHi[k] = k < nb ? dzt.hi[k] : 0.0;
+      sDzSc[k] = k < nb ? dzt.scale[k] : 0.0;
+    }
   }
   {
     unsigned long long* z = reinterpret_cast<unsigned long long*>(acc_raw);
@@ -485,7 +494,19 @@ pair_hist_kernel(const double* __restrict__ coords, const double* __restrict__ v
           } else {
             dz[r] = zi[r] - zj;
           }
-          if (STATS == 4) dz[r] = (fabs(dz[r]) < sDzLo[min(gg, nbS - GS) / GS]) ? 1.0 : 0.0;
+          if (STATS == 4) {
+            const double ad = fabs(dz[r]);
+            const unsigned lg = min(gg, nbS - GS) / GS;
+            const double lo = sDzLo[lg];
+            // the few in-window keys also go to the fine histogram of the median select (one
+            // sweep instead of a count sweep plus a histogram sweep)
+            if (whist && gg < nbS && ad >= lo && ad < sDzHi[lg]) {
+              long long bk = __double2ll_rz(__dmul_rn(__dsub_rn(ad, lo), sDzSc[lg]));
+              bk = bk < wbuckets - 1 ? bk : wbuckets - 1;
+              atomicAdd(&whist[(long long)lg * wbuckets + bk], 1ull);
+            }
+            dz[r] = (ad < lo) ? 1.0 : 0.0;
+          }
         }
       };
       auto accumulate = [&](const unsigned (&g)[HR], const double (&dz)[HR]) {
@@ -844,6 +865,8 @@ struct HistLaunch {
   int max_blocks; int64_t ntiles; int js; size_t smem; cudaStream_t st; int* nblocks_out;
   MvSpec mv;
   const double* bbox8;
+  unsigned long long* whist;  // STATS == 4: optional in-window |dz| histogram [n_lags][wbuckets]
+  long long wbuckets;
 };
 
 template <int DIM, int DIR, int STATS, int EMAX, bool PRIV, bool VM>
@@ -866,7 +889,7 @@ static int launch_hist(const HistLaunch& L) {
   *L.nblocks_out = (int)grid;
   kern<<<(unsigned)grid, HB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, *L.dp, L.partial,
                                              L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi,
-                                             *L.dzt, js, L.mv);
+                                             *L.dzt, js, L.mv, L.whist, L.wbuckets);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

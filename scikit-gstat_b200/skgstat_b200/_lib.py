@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SKG_B200_LIB") or os.path.join(_HERE, "libskg_b200.so")  # env: developer builds
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 TILE = 256
 MAX_LAGS = 250
 KRIGE_MAX_POINTS = 64
@@ -45,6 +45,8 @@ SIGNATURES = {
     "skg_pair_scratch_bytes": (_i64, [_i64, _int]),
     "skg_pair_hist": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _i64,
                              _i64, _i64, _i64, _p]),
+    "skg_pair_dz_windows": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _p, _p, _p, _i64, _p, _p, _p, _p,
+                                   _i64, _i64, _i64, _i64, _p]),
     "skg_pair_batch_max_lags": (_int, []),
     "skg_pair_batch_scratch_bytes": (_i64, [_i64, _int]),
     "skg_pair_hist_batch": (_int, [_p, _p, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,

@@ -234,6 +234,7 @@ class PairEngine:
                                  % (_lib.MAX_VALUE_COLUMNS, k))
         v = np.ascontiguousarray(v)
         self._orig_values = v
+        self._values_version = getattr(self, "_values_version", 0) + 1
         self.nv = 1 if v.ndim == 1 else int(v.shape[1])
         self.vmode = value_mode
         cols = np.ascontiguousarray(v.T).reshape(self.nv, self.n)        # device layout [k][n]
@@ -635,23 +636,41 @@ class PairEngine:
             s = D.allgather_varlen(slots, self.group)
             if want is None:
                 return to_host(k), to_host(s).view(np.uint32).astype(np.int64)
-            picks, layout = [], []
-            for slot, rel in want:
-                sl32 = int(np.array([slot], dtype=np.uint32).view(np.int32)[0])
-                srt = torch.sort(k[s == sl32]).values
-                idx = torch.tensor([min(r, max(srt.numel() - 1, 0)) for r in rel], dtype=torch.int64,
-                                   device=self.device)
-                vals = srt[idx] if srt.numel() else torch.zeros(len(rel), dtype=torch.float64,
-                                                                device=self.device)
-                picks.append(torch.cat([torch.tensor([float(srt.numel())], dtype=torch.float64,
-                                                     device=self.device), vals]))
-                layout.append((slot, list(rel)))
-            flat = to_host(torch.cat(picks)) if picks else np.zeros(0)
-            out, pos = {}, 0
-            for slot, rel in layout:
-                cnt_slot = int(flat[pos])
-                out[slot] = (cnt_slot, {r: float(flat[pos + 1 + i]) for i, r in enumerate(rel)})
-                pos += 1 + len(rel)
+            # all wanted order statistics with a constant number of device operations: sort by key,
+            # stable sort by slot, segment starts from a searchsorted, one gather, one copy back
+            if not want:
+                return {}
+            slots_w = torch.tensor([int(np.array([slot], dtype=np.uint32).view(np.int32)[0]) for slot, _ in want],
+                                   dtype=torch.int32, device=self.device)
+            if k.numel():
+                k_sorted, order = torch.sort(k)
+                s_sorted, order2 = torch.sort(s[order], stable=True)
+                k_sorted = k_sorted[order2]
+                start = torch.searchsorted(s_sorted, slots_w, right=False)
+                stop = torch.searchsorted(s_sorted, slots_w, right=True)
+            else:
+                k_sorted = torch.zeros(1, dtype=torch.float64, device=self.device)
+                start = torch.zeros(len(want), dtype=torch.int64, device=self.device)
+                stop = start
+            cnt_slot = (stop - start)
+            rel_flat, seg_of = [], []
+            for w, (slot, rel) in enumerate(want):
+                rel_flat += [int(r) for r in rel]
+                seg_of += [w] * len(rel)
+            if rel_flat:
+                seg_t = torch.tensor(seg_of, dtype=torch.int64, device=self.device)
+                rel_t = torch.tensor(rel_flat, dtype=torch.int64, device=self.device)
+                idx = start[seg_t] + torch.minimum(rel_t, torch.clamp(cnt_slot[seg_t] - 1, min=0))
+                idx = torch.clamp(idx, 0, max(int(k_sorted.numel()) - 1, 0))
+                vals = k_sorted[idx]
+            else:
+                vals = torch.zeros(0, dtype=torch.float64, device=self.device)
+            flat = to_host(torch.cat([cnt_slot.to(torch.float64), vals]))
+            nw = len(want)
+            out, pos = {}, nw
+            for w, (slot, rel) in enumerate(want):
+                out[slot] = (int(flat[w]), {r: float(flat[pos + i]) for i, r in enumerate(rel)})
+                pos += len(rel)
             return out
 
         run_gather.device_pick = True
@@ -736,6 +755,7 @@ class PairEngine:
         if self._sub_engine is None:
             m = min(self.n, self.SUBSAMPLE_POINTS)
             idx = np.sort(np.random.default_rng(777).choice(self.n, size=m, replace=False))
+            self._sub_idx = idx
             self._sub_engine = PairEngine(self._orig_coords[idx], None, device=self.device)
         return self._sub_engine
 
@@ -979,11 +999,65 @@ class PairEngine:
     WINDOWED_MEDIAN_MIN_PAIRS = 2 * 10 ** 8   # below this the plain two-sweep select is fast enough
     WINDOW_HALF_QUANTILE = 0.04
 
-    def _dz_select(self, thr, dirp, lo_bits, hi_bits, rank_fn, n_keys=None):
+    def _dz_select(self, thr, dirp, lo_bits, hi_bits, rank_fn, n_keys=None, first_hist=None, nb=None):
+        """first_hist: the histogram of the first pass if a merged sweep already produced it (same
+        windows, scales and bucket count as exact_select's first request)."""
         nl = int(thr.size)
-        nb = self._buckets_for(self.n_pairs if n_keys is None else n_keys, nl)
+        if nb is None:
+            nb = self._buckets_for(self.n_pairs if n_keys is None else n_keys, nl)
         rh, rg = self._select_runner(_lib.KEY_ABSDZ, thr, dirp, nb)
+        if first_hist is not None:
+            calls = []
+
+            def rh_first(lo, hi, sc, _rh=rh):
+                if calls:
+                    return _rh(lo, hi, sc)
+                calls.append(1)
+                return first_hist
+            rh = rh_first
         return exact_select(nl, lo_bits, hi_bits, nb, rank_fn, rh, rg)
+
+    def dz_windows(self, thr: np.ndarray, w_lo: np.ndarray, w_hi: np.ndarray, n_buckets: int, dirp=None):
+        """One sweep (skg_pair_dz_windows): per lag class the exact pair count, the count of pairs with
+        |dz| below the class's window [w_lo, w_hi) (bit patterns) and the bucket histogram of the
+        |dz| inside the window - the first two passes of the windowed Dowd median in one."""
+        from .select import _scale_for
+        nl = int(thr.size)
+        w_lo = np.ascontiguousarray(w_lo, dtype=np.uint64)
+        w_hi = np.ascontiguousarray(w_hi, dtype=np.uint64)
+        sc = np.array([_scale_for(int(a), int(b), n_buckets) if b > a else 0.0 for a, b in zip(w_lo, w_hi)])
+        cnt = self._buffer("hist_cnt", nl, torch.int64).zero_()
+        below = self._buffer("hist_below", nl, torch.float64).zero_()
+        hist = self._buffer("select_hist", nl * n_buckets, torch.int64).zero_()
+        scratch = self._hist_scratch(nl)
+        with torch.cuda.device(self.device):
+            rc = self.lib.skg_pair_dz_windows(
+                _ptr(self.coords), _ptr(self.values), self.nv, self.vmode, self.n, self.dim, _hptr(dirp), _hptr(thr),
+                nl, _hptr(w_lo), _hptr(w_hi), _hptr(sc), n_buckets, _ptr(cnt), _ptr(below), _ptr(hist),
+                _ptr(scratch), scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
+        _lib.check(rc, "skg_pair_dz_windows")
+        self.launches += 5 if self.t1 > self.t0 else 0
+        both = torch.cat([cnt.to(torch.float64), below])
+        amb = self.ambiguous_pairs(dirp)
+        if amb is not None and amb[0].size:
+            s_bits, dz = self._amb_keys(amb)
+            g = np.searchsorted(thr, s_bits, side="right")
+            keep = g < nl
+            g, dz = g[keep], dz[keep]
+            lo_v, kb = w_lo.view(np.float64), np.ascontiguousarray(dz).view(np.uint64)
+            extra = np.zeros(2 * nl)
+            np.add.at(extra, g, 1.0)
+            np.add.at(extra, nl + g, (dz < lo_v[g]).astype(float))
+            both += to_device(extra, self.device)
+            inside = (kb >= w_lo[g]) & (kb < w_hi[g])
+            t = (dz[inside] - lo_v[g[inside]]) * sc[g[inside]]
+            b = np.minimum(n_buckets - 1, np.where(t >= 9.0e18, n_buckets - 1, t).astype(np.int64))
+            hist += to_device(np.bincount(g[inside] * n_buckets + b, minlength=nl * n_buckets).astype(np.int64),
+                              self.device)
+        D.allreduce_sum_(both, self.group)
+        D.allreduce_sum_(hist, self.group)
+        host = to_host(both)
+        return host[:nl].astype(np.int64), host[nl:].astype(np.int64), to_host(hist).reshape(nl, n_buckets), sc
 
     def hist_below(self, thr: np.ndarray, dz_lo: np.ndarray, dirp=None):
         """Exact per-lag (pair count, count of pairs with |dz| < dz_lo[lag]) with the fused-pass
@@ -1115,8 +1189,15 @@ class PairEngine:
             win = self._median_windows(thr, dirp, hi)
             if win is not None:
                 w_lo, w_hi = win                      # per-lag bit windows [lo, hi)
-                dz_lo = w_lo.view(np.float64)
-                counts, below = self.hist_below(thr, dz_lo, dirp)
+                if fsrc is None:
+                    # one sweep: counts, below-window counts and the in-window histogram
+                    nbk = 1 << 12
+                    with _phase("dz windows sweep"):
+                        counts, below, hist0, _ = self.dz_windows(thr, w_lo, w_hi, nbk, dirp)
+                else:
+                    dz_lo = w_lo.view(np.float64)
+                    counts, below = self.hist_below(thr, dz_lo, dirp)
+                    hist0, nbk = None, None
                 ra = (counts - 1) // 2 - below       # ranks relative to the window start
                 rb = counts // 2 - below
 
@@ -1129,7 +1210,8 @@ class PairEngine:
                 # histogram (device memory, D2H copy, host prefix sums) for that population
                 vals, wtot = self._dz_select(thr, dirp, [int(x) for x in w_lo],
                                              [int(x) for x in w_hi], rel_rank_fn,
-                                             n_keys=int(counts.sum() * 2.5 * self.WINDOW_HALF_QUANTILE) + 1)
+                                             n_keys=int(counts.sum() * 2.5 * self.WINDOW_HALF_QUANTILE) + 1,
+                                             first_hist=hist0, nb=nbk)
                 totals = [int(c) for c in counts]
                 med_lo = [None] * nl
                 med_hi = [None] * nl
@@ -1165,12 +1247,12 @@ class PairEngine:
         0.5 -/+ WINDOW_HALF_QUANTILE quantiles of a random sub-sample of the points.  The same
         sample (fixed seed) on every rank, so all ranks use identical windows."""
         nl = int(thr.size)
-        m = int(min(self.n, max(4000, self.n // 4)))
-        if m >= self.n:
+        if self.n <= self.SUBSAMPLE_POINTS:
             return None
-        idx = np.sort(np.random.default_rng(12345).choice(self.n, size=m, replace=False))
-        sub = PairEngine(self._orig_coords[idx], self._orig_values[idx], device=self.device,
-                         value_mode=self.vmode)
+        sub = self._subsample_engine()
+        if getattr(sub, "_parent_values_version", None) != self._values_version or sub.vmode != self.vmode:
+            sub.set_values(self._orig_values[self._sub_idx], self.vmode)
+            sub._parent_values_version = self._values_version
         sub.pair_filter = self.pair_filter
         q = self.WINDOW_HALF_QUANTILE
 
@@ -1179,8 +1261,11 @@ class PairEngine:
                 return []
             return [max(0, int((0.5 - q) * tot)), min(tot - 1, int((0.5 + q) * tot))]
 
-        vals, totals = sub._dz_select(thr, dirp, [0] * nl, [hi_bits_full] * nl, rank_fn)
+        with _phase("dz sub-sample select"):
+            vals, totals = sub._dz_select(thr, dirp, [0] * nl, [hi_bits_full] * nl, rank_fn)
         self.launches += sub.launches
+        sub.launches = 0
+        sub.pair_filter = None
         w_lo = np.zeros(nl, dtype=np.uint64)
         w_hi = np.full(nl, hi_bits_full, dtype=np.uint64)
         for g in range(nl):
