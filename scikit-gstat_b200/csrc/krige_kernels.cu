@@ -804,6 +804,7 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
       for (int k = kb; k < ke; ++k) {
         const int ok = k * (k + 1) / 2;
         const double akk = L[ok + k];
+        __syncwarp();  // every lane holds the pivot before lane 0 overwrites it below
         if (!(akk > 0.0)) { bad = true; break; }
         const double rd = rsqrt(akk);
         for (int i = k + 1 + lane; i < R; i += 32) {

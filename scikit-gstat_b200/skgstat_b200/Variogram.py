@@ -962,16 +962,21 @@ class Variogram:
 
     @property
     def rmse(self):
-        exp, mod = self.experimental, self.fitted_model(self.bins)
-        return np.sqrt(np.nansum((mod - exp) ** 2) / len(mod))
+        """Variogram.py:2300-2321: the reference returns root_mean_square (nanmean over the lag classes
+        that hold pairs)."""
+        return self.root_mean_square
 
     @property
     def mse(self):
-        return np.nanmean(np.power(self.model_residuals, 2))
+        """Variogram.py:2326-2352: np.mean - an empty lag class (NaN) makes it NaN, as upstream."""
+        experimental, model = self.model_deviations()
+        return np.mean(np.power(np.subtract(experimental, model), 2))
 
     @property
     def mae(self):
-        return np.nanmean(np.abs(self.model_residuals))
+        """Variogram.py:2358-2384: np.mean, NaN with an empty lag class."""
+        experimental, model = self.model_deviations()
+        return np.mean(np.abs(np.subtract(experimental, model)))
 
     @property
     def nrmse(self):

@@ -48,6 +48,15 @@ def allreduce_max_(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def allreduce_max_int(value: int, device, group=None) -> int:
+    """max over the ranks of a host integer (error decisions must be collective)."""
+    if world(group)[1] == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
 def allgather_varlen(t: torch.Tensor, group=None) -> torch.Tensor:
     """Concatenate 1-D tensors of different lengths from all ranks (rank order)."""
     rank, ws = world(group)

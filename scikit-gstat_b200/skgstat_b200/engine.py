@@ -370,7 +370,11 @@ class PairEngine:
         _lib.check(rc, "skg_pair_dir_ambiguous")
         self.launches += 4 if t1 > t0 else 0
         got = int(cnt.item())
-        if got > cap:
+        # a rank-local raise would leave the other ranks waiting in the next collective: agree on
+        # the worst count first, then every rank raises
+        worst = got if (all_tiles or self.world == 1) else D.allreduce_max_int(got, self.device, self.group)
+        if worst > cap:
+            got = worst
             raise RuntimeError(
                 "%d point pairs lie exactly on the directional decision boundary (more than "
                 "%d): lattice data with a round azimuth/tolerance; not supported" % (got, cap))
@@ -623,8 +627,9 @@ class PairEngine:
             _lib.check(rc, "skg_pair_select_gather")
             self.launches += 4 if self.t1 > self.t0 else 0
             got = int(cnt.item())
-            if got > cap:
-                raise RuntimeError("gather overflow: %d > %d" % (got, cap))
+            worst = got if self.world == 1 else D.allreduce_max_int(got, self.device, self.group)
+            if worst > cap:   # decided collectively, so every rank raises (no rank is left in a collective)
+                raise RuntimeError("gather overflow: %d > %d" % (worst, cap))
             keys, slots = keys[:got], slots[:got]
             if amb_key is not None and amb_key.size:
                 k, sl = amb_slots(lo, hi, sc)

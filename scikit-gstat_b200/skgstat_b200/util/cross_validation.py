@@ -22,15 +22,39 @@ def leave_one_out(variogram, indices=None, min_points=5, max_points=15, coordina
     if indices is None:
         indices = np.arange(len(c))
     indices = np.asarray(indices, dtype=np.int64)
-    if len(np.unique(c, axis=0)) != len(c):
-        raise NotImplementedError("jacknife with duplicated sample coordinates is not built "
-                                  "(the reference de-duplicates after removing the point)")
-    ok = OrdinaryKriging(variogram, min_points=min_points, max_points=max_points,
-                         coordinates=c, values=v)
-    eng = ok._engine()
-    z, sigma, status = eng.transform(c[indices], ok._model_name, ok._model_params(),
-                                     ok._minp, ok._maxp, exclude=indices.astype(np.int32))
-    return z - v[indices].astype(np.float64)
+    # co-located samples: the reference removes the point and THEN de-duplicates
+    # (util/cross_validation.py:9-21 -> OrdinaryKriging._remove_duplicated_coordinates), so the
+    # target keeps a neighbour at distance zero.  Those (rare) targets are kriged one at a time on
+    # the sample set without the point, exactly as upstream; all others share one batched call.
+    _, inverse, counts = np.unique(c, axis=0, return_inverse=True, return_counts=True)
+    dup_point = counts[np.ravel(inverse)] > 1
+    out = np.full(len(indices), np.nan)
+    plain = ~dup_point[indices]
+    if plain.any():
+        if dup_point.any():
+            # with twins present the batch runs on the de-duplicated set (first occurrences, as the
+            # reference keeps) and excludes each target by its position in that set
+            first = np.sort(np.unique(c, axis=0, return_index=True)[1])
+            pos = -np.ones(len(c), dtype=np.int64)
+            pos[first] = np.arange(first.size)
+            cs, vs = c[first], v[first]
+        else:
+            pos = np.arange(len(c))
+            cs, vs = c, v
+        ok = OrdinaryKriging(variogram, min_points=min_points, max_points=max_points,
+                             coordinates=cs, values=vs)
+        eng = ok._engine()
+        idx = indices[plain]
+        z, sigma, status = eng.transform(c[idx], ok._model_name, ok._model_params(),
+                                         ok._minp, ok._maxp, exclude=pos[idx].astype(np.int32))
+        out[plain] = z - v[idx].astype(np.float64)
+    for k in np.flatnonzero(~plain):
+        i = int(indices[k])
+        ok = OrdinaryKriging(variogram, min_points=min_points, max_points=max_points,
+                             coordinates=np.delete(c, i, axis=0), values=np.delete(v, i))
+        z = ok.transform(*[np.atleast_1d(x) for x in c[i]])
+        out[k] = float(z[0]) - float(v[i])
+    return out
 
 
 def jacknife(variogram, n=None, metric="rmse", seed=None):

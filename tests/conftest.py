@@ -18,6 +18,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device the gpu-marked tests are skipped (plain `pytest tests` on a CPU box);
+    on the GPU box they run and fail loudly if the library cannot be loaded."""
+    if has_cuda():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 class Golden:
     """Lazy view on one golden npz (reference outputs, see oracle/make_golden.py)."""
 

@@ -67,3 +67,27 @@ def test_leave_one_out_against_oracle_3d(skg):
         dev = leave_one_out(d, idx, min_points=4, max_points=20, coordinates=c, values=v)
     ref = okr.jacknife_deviations(c, v, idx, "exponential", 25.0, 4.0, 0.2, None, 4, 20)
     assert_allclose(dev, ref, rtol=1e-9, atol=1e-10, equal_nan=True)
+
+
+def test_leave_one_out_with_colocated_samples(skg):
+    """duplicated coordinates - the reference removes the point, then de-duplicates
+    (util/cross_validation.py:9-21); the drop-in follows it literally for the affected targets."""
+    from oracle import kriging as okr
+    from skgstat_b200.util import cross_validation as cv
+    rng = np.random.default_rng(4)
+    c = rng.random((120, 2)) * 100
+    v = rng.normal(size=120)
+    c[7] = c[3]          # twins with different observations
+    c[50] = c[3]
+    c[90] = c[61]
+    V = skg.Variogram(c, v, model="exponential", n_lags=10, maxlag="median")
+    idx = np.array([0, 3, 7, 50, 61, 90, 100])
+    got = cv.leave_one_out(V, idx)
+    d = V.describe()
+    for k, i in enumerate(idx):
+        cc, vv = np.delete(c, i, axis=0), np.delete(v, i)
+        _, first = np.unique(cc, axis=0, return_index=True)
+        first.sort()
+        zr, _, _ = okr.krige(cc[first], vv[first], c[i][None, :], "exponential", d["effective_range"],
+                             d["sill"], d["nugget"], None, 5, 15)
+        np.testing.assert_allclose(got[k], zr[0] - v[i], rtol=1e-8, atol=1e-10)

@@ -10,6 +10,7 @@ scaling laws of the estimators, permutation invariance (exact counts), direction
 symmetry, kriging exactness at the samples / constant-field reproduction / translation
 invariance, plus spot checks of sub-blocks against the row-blocked oracle.
 """
+import os
 import warnings
 
 import numpy as np
@@ -163,3 +164,46 @@ def test_config5_kriging_grid_2000x2000(skg):
         warnings.simplefilter("ignore")
         zt = okt.transform(gx[::997] + 12345.0, gy[::997] + 12345.0)
     assert_allclose(zt, z[::997], rtol=1e-7)
+
+
+# ---- full-size pins: oracle-only golden vectors (oracle/make_fullsize_golden.py) ----------------
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.npz")
+
+
+@pytest.fixture(scope="module")
+def fullsize_golden():
+    if not os.path.exists(GOLDEN):
+        pytest.skip("tests/golden/fullsize.npz not generated")
+    return np.load(GOLDEN)
+
+
+def test_config3_200k_pinned_to_cpu_oracle(skg, field200k, fullsize_golden):
+    """N = 200 000 (2e10 pairs): the exact median maxlag, bit-exact edges and per-lag pair counts and
+    1e-12 semivariances of matheron / cressie / dowd against the C oracle's sweep over ALL pairs
+    (edges from the oracle's own exact select, integer counts, long-double sums)."""
+    g = fullsize_golden
+    c, v = field200k
+    assert int(g["c3_n"]) == len(c)
+    for est in ("matheron", "cressie", "dowd"):
+        V = skg.Variogram(c, v, estimator=est, n_lags=25, maxlag="median", fit_method=None)
+        assert V.maxlag == float(g["c3_maxlag"])
+        assert_array_equal(V.bins, g["c3_bins"])
+        assert_array_equal(V.bin_count, g["c3_bin_count"])
+        assert_allclose(V.experimental, g["c3_" + est], rtol=1e-12, atol=0)
+
+
+def test_config4_100k_directional_pinned_to_cpu_oracle(skg, fullsize_golden):
+    """N = 100 000 directional (azimuth 45, tolerance 22.5, q33 bandwidth, uniform bins): bandwidth,
+    bit-exact uniform edges and counts, 1e-12 semivariances against the C oracle, whose mask is the
+    reference's literal arccos / sin formula evaluated for every one of the 5e9 pairs."""
+    g = fullsize_golden
+    n = int(g["c4_n"])
+    c = random_points(n, 10000.0, 2, seed=4)
+    v = gaussian_field(c, 800.0, seed=4)
+    DV = skg.DirectionalVariogram(c, v, azimuth=45, tolerance=22.5, bin_func="uniform", n_lags=10,
+                                  fit_method=None)
+    assert DV.bandwidth == float(g["c4_bandwidth"])
+    assert_array_equal(DV.bins, g["c4_bins"])
+    assert_array_equal(DV.bin_count, g["c4_bin_count"])
+    assert_allclose(DV.experimental, g["c4_matheron"], rtol=1e-12, atol=0)
