@@ -318,14 +318,22 @@ int skg_krige_build_grid(const double* coords, int64_t n, int dim, const double*
  *   The solve is a Cholesky factorisation of the covariance form of the system on
  *   the FP64 tensor cores; targets whose covariance matrix is not positive
  *   definite in fp64 are re-solved by partial-pivot LU of the original system.
+ *   sample_cov [dev, n*n] or NULL: c_t - gamma(d_ij) of ALL sample pairs, filled once per sample
+ *   set and model by skg_krige_sample_cov.  The kriging matrix of a target only holds
+ *   sample-to-sample entries, so with the cache its build is a gather (rows of neighbouring
+ *   targets stay L2-resident) instead of n(n-1)/2 distance + model evaluations - the same idea as
+ *   the reference's cached N x N sample distances (MetricSpace.diagonal, MetricSpace.py:158-187).
+ *   Bit-identical results with and without the cache.
  */
+int skg_krige_sample_cov(const double* coords, int64_t n, int dim, int model, const double* model_params,
+                         const double* matrix_lut, int lut_size, double* cov, void* stream);
 int64_t skg_krige_scratch_bytes(int max_points);
 int skg_krige(const double* coords, const double* values, int64_t n, int dim,
               const double* grid, const int32_t* cell_start, const int32_t* order,
               const double* targets, int64_t m, int model, const double* model_params,
               const double* matrix_lut, int lut_size,
               double radius, int min_points, int max_points, const int32_t* exclude,
-              double* z, double* sigma, int32_t* status,
+              const double* sample_cov, double* z, double* sigma, int32_t* status,
               void* scratch, int64_t scratch_bytes,
               int64_t target_begin, int64_t target_end, void* stream);
 

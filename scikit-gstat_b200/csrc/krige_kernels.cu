@@ -273,6 +273,7 @@ struct KrigeArgs {
   int region_bytes;  // per-warp shared region (list, later the matrix)
   int retry_only;    // LU kernel: only targets the Cholesky kernel marked KRIGE_RETRY
   const int* exclude;  // per target: sample id that must not be a neighbour (-1: none), or NULL
+  const double* sample_cov;  // [n][n] c_t - gamma_matrix(d_ij) of all sample pairs (skg_krige_sample_cov) or NULL
 };
 
 constexpr int KRIGE_RETRY = 3;  // internal: covariance matrix not positive definite in fp64
@@ -696,17 +697,19 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int maxp = a.max_points;
-  // per-warp layout: region | nbr coords [DIM][maxp] | values | gamma(d_0i) | col [maxp+2] | x [maxp]
-  const int per_warp = a.region_bytes + (DIM + 3) * maxp * 8 + (maxp + 2) * 8;
+  // per-warp layout: region | values | gamma(d_0i) | x [maxp] (its space first holds the neighbour
+  // ids) | nbr coords [DIM][maxp] (only without the sample-covariance cache)
+  const bool cached = a.sample_cov != nullptr;
+  const int per_warp = a.region_bytes + 3 * maxp * 8 + (cached ? 0 : DIM * maxp * 8);
   unsigned char* base = smem_raw + (size_t)warp * per_warp;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
   int* ids = reinterpret_cast<int*>(base + (size_t)a.cap * 8);
   double* L = reinterpret_cast<double*>(base);
-  double* ncoord = reinterpret_cast<double*>(base + a.region_bytes);
-  double* nval = ncoord + DIM * maxp;
+  double* nval = reinterpret_cast<double*>(base + a.region_bytes);
   double* gvec = nval + maxp;
   double* xv = gvec + maxp;
-  double* col = xv + maxp;
+  int* nid = reinterpret_cast<int*>(xv);  // neighbour sample ids: dead before x is written
+  double* ncoord = xv + maxp;
 
   const double* __restrict__ X = a.coords;
   const double* __restrict__ Y = a.coords + a.n;
@@ -744,12 +747,15 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     for (int q = 0; q < 2; ++q) {
       const int e = lane + 32 * q;
       if (e < n) {
-        ncoord[e] = X[kid[q]];
-        ncoord[maxp + e] = Y[kid[q]];
-        if (DIM == 3) ncoord[2 * maxp + e] = W[kid[q]];
+        if (!cached) {
+          ncoord[e] = X[kid[q]];
+          ncoord[maxp + e] = Y[kid[q]];
+          if (DIM == 3) ncoord[2 * maxp + e] = W[kid[q]];
+        }
         nval[e] = a.values[kid[q]];
         const double gv = gamma_model(kd[q], a.model);  // Kriging.py:611-613
         gvec[e] = gv;
+        nid[e] = kid[q];
         L[prow(e, n) + e] = ct;  // C_ii = c_t - 0 (zero diagonal of the gamma matrix, :600)
         L[rowc + e] = ct - gv;
         L[rowo + e] = 1.0;
@@ -757,6 +763,33 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     }
     __syncwarp();
     const int npairs = n * (n - 1) / 2;
+    if (a.sample_cov) {
+      // the sample-sample entries do not depend on the target: gather them from the cached
+      // covariance matrix (the reference caches the N x N sample distances the same way,
+      // MetricSpace.py:158-187) instead of 2016 distance + model evaluations per target.  Rows
+      // of adjacent targets' neighbours stay L2-resident.
+      const double* __restrict__ cov = a.sample_cov;
+      // four rows per step: up to four independent L2 loads in flight per lane
+      for (int j = 1; j < n; j += 4) {
+        int jj[4], oo[4];
+        const double* rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          jj[u] = j + u < n ? j + u : n - 1;
+          rr[u] = cov + (int64_t)nid[jj[u]] * a.n;
+          oo[u] = prow(jj[u], n);
+        }
+        for (int i = lane; i < jj[3]; i += 32) {
+          const int id = nid[i];
+          double cv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cv[u] = rr[u][id];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i < jj[u] && j + u < n) L[oo[u] + i] = cv[u];
+        }
+      }
+    } else
     for (int p0 = lane; p0 < npairs; p0 += 64) {
       int pi[2], pj[2];
       double cv[2];
@@ -909,6 +942,32 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
   }
 }
 
+// c_t - gamma_matrix(d_ij) for every sample pair, with the arithmetic of the per-target build
+// (same device functions, same operand order; s is symmetric in (i, j) bit for bit)
+template <int DIM>
+__global__ void __launch_bounds__(256)
+krige_sample_cov_kernel(const double* __restrict__ coords, int64_t n, const __grid_constant__ ModelParams model,
+                        double* __restrict__ cov) {
+  const double ct = model.b + model.c0;
+  const double* __restrict__ X = coords;
+  const double* __restrict__ Y = coords + n;
+  const double* __restrict__ W = coords + 2 * n;
+  const int64_t total = n * n;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = k / n, j = k - i * n;
+    if (i == j) { cov[k] = ct; continue; }
+    const double dx = X[i] - X[j];
+    const double dy = Y[i] - Y[j];
+    double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (DIM == 3) {
+      const double dw = W[i] - W[j];
+      s = __dadd_rn(s, __dmul_rn(dw, dw));
+    }
+    cov[k] = ct - gamma_matrix(sqrt(s), model);
+  }
+}
+
 static int parse_grid(const double* grid, int dim, GridParams* g) {
   if (!grid) { set_error("grid NULL"); return SKG_E_BADARG; }
   g->ox = grid[0]; g->oy = grid[1]; g->oz = grid[2]; g->h = grid[3];
@@ -931,20 +990,20 @@ static void krige_layout(int max_points, int dim, int* cap, int* region, int* pe
   *per_warp = reg + (dim + 1) * max_points * 8 + 2 * (max_points + 1) * 8;
 }
 
-static void krige_chol_layout(int max_points, int dim, int* cap, int* region, int* per_warp) {
+static void krige_chol_layout(int max_points, int dim, bool cached, int* cap, int* region, int* per_warp) {
   const int n = max_points;
   int reg = (n * (n + 1) / 2 + 2 * n) * 8;
   reg = std::max(reg, 1024 * 12);
   reg = (reg + 15) & ~15;
   *cap = reg / 12;
   *region = reg;
-  *per_warp = reg + (dim + 3) * n * 8 + (n + 2) * 8;
+  *per_warp = reg + 3 * n * 8 + (cached ? 0 : dim * n * 8);
 }
 
 // warps per CTA that maximise resident warps per SM for a given per-warp footprint
-static int best_wpb(int per_warp, int smem_budget) {
+static int best_wpb(int per_warp, int smem_budget, int max_w) {
   int best = 0, best_w = 1;
-  for (int w = 8; w >= 1; --w) {
+  for (int w = max_w; w >= 1; --w) {
     if ((size_t)w * per_warp > (size_t)smem_budget) continue;
     const int ctas = std::min(32, smem_budget / (w * per_warp + 1024));
     const int resident = std::min(64, ctas * w);
@@ -989,6 +1048,48 @@ int skg_krige_build_grid(const double* coords, int64_t n, int dim, const double*
   return 0;
 }
 
+static int fill_model(int model, const double* model_params, const double* matrix_lut, int lut_size,
+                      ModelParams* mp) {
+  if (model < SKG_MODEL_SPHERICAL || model > SKG_MODEL_MATERN) { set_error("unknown model id %d", model); return SKG_E_BADARG; }
+  if ((matrix_lut != nullptr) != (lut_size > 0)) { set_error("matrix_lut and lut_size must come together"); return SKG_E_BADARG; }
+  std::memset(mp, 0, sizeof(*mp));
+  mp->model = model;
+  mp->r = model_params[0]; mp->c0 = model_params[1];
+  mp->s = model_params[2]; mp->b = model_params[3];
+  switch (model) {
+    case SKG_MODEL_SPHERICAL: mp->a = mp->r / 1.0; break;
+    case SKG_MODEL_EXPONENTIAL: mp->a = mp->r / 3.0; break;
+    case SKG_MODEL_GAUSSIAN: mp->a = mp->r / 2.0; break;
+    case SKG_MODEL_CUBIC: mp->a = mp->r / 1.0; break;
+    case SKG_MODEL_MATERN:
+      mp->a = mp->r / 2.0;
+      mp->gnorm = 2.0 / std::tgamma(mp->s);
+      break;
+    default: mp->a = mp->r / std::pow(3.0, 1.0 / mp->s); break;
+  }
+  mp->lut = matrix_lut;
+  mp->lut_size = lut_size;
+  mp->lut_range = model_params[4];
+  mp->lut_out = model_params[5];
+  return 0;
+}
+
+int skg_krige_sample_cov(const double* coords, int64_t n, int dim, int model, const double* model_params,
+                         const double* matrix_lut, int lut_size, double* cov, void* stream) {
+  if (!coords || !model_params || !cov || n < 1) { set_error("NULL argument or n < 1"); return SKG_E_BADARG; }
+  if (dim != 2 && dim != 3) { set_error("dim=%d unsupported", dim); return SKG_E_UNSUPPORTED; }
+  ModelParams mp;
+  int rc = fill_model(model, model_params, matrix_lut, lut_size, &mp);
+  if (rc) return rc;
+  const int64_t blocks = std::min<int64_t>((n * n + 255) / 256, (int64_t)sm_count() * 32);
+  if (dim == 3)
+    krige_sample_cov_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(coords, n, mp, cov);
+  else
+    krige_sample_cov_kernel<2><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(coords, n, mp, cov);
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int64_t skg_krige_scratch_bytes(int max_points) {
   (void)max_points;
   return 16;  // the warp-per-target kernel keeps everything in shared memory
@@ -997,7 +1098,8 @@ int64_t skg_krige_scratch_bytes(int max_points) {
 int skg_krige(const double* coords, const double* values, int64_t n, int dim, const double* grid,
               const int32_t* cell_start, const int32_t* order, const double* targets, int64_t m,
               int model, const double* model_params, const double* matrix_lut, int lut_size,
-              double radius, int min_points, int max_points, const int32_t* exclude, double* z, double* sigma, int32_t* status, void* scratch,
+              double radius, int min_points, int max_points, const int32_t* exclude,
+              const double* sample_cov, double* z, double* sigma, int32_t* status, void* scratch,
               int64_t scratch_bytes, int64_t target_begin, int64_t target_end, void* stream) {
   (void)scratch; (void)scratch_bytes;
   if (!coords || !values || !cell_start || !order || !targets || !model_params || !z || !sigma || !status) {
@@ -1014,46 +1116,29 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
     return SKG_E_UNSUPPORTED;
   }
   if (min_points < 0 || min_points > max_points) { set_error("min_points outside [0, max_points]"); return SKG_E_BADARG; }
-  if (model < SKG_MODEL_SPHERICAL || model > SKG_MODEL_MATERN) { set_error("unknown model id %d", model); return SKG_E_BADARG; }
-  if ((matrix_lut != nullptr) != (lut_size > 0)) { set_error("matrix_lut and lut_size must come together"); return SKG_E_BADARG; }
   if (!(radius >= 0.0)) { set_error("radius must be >= 0"); return SKG_E_BADARG; }
   KrigeArgs a;
   std::memset(&a, 0, sizeof(a));
   int rc = parse_grid(grid, dim, &a.grid);
   if (rc) return rc;
+  rc = fill_model(model, model_params, matrix_lut, lut_size, &a.model);
+  if (rc) return rc;
   a.coords = coords; a.values = values; a.n = n;
   a.cell_start = cell_start; a.order = order; a.targets = targets; a.m = m;
-  a.model.model = model;
-  a.model.r = model_params[0]; a.model.c0 = model_params[1];
-  a.model.s = model_params[2]; a.model.b = model_params[3];
-  switch (model) {
-    case SKG_MODEL_SPHERICAL: a.model.a = a.model.r / 1.0; break;
-    case SKG_MODEL_EXPONENTIAL: a.model.a = a.model.r / 3.0; break;
-    case SKG_MODEL_GAUSSIAN: a.model.a = a.model.r / 2.0; break;
-    case SKG_MODEL_CUBIC: a.model.a = a.model.r / 1.0; break;
-    case SKG_MODEL_MATERN:
-      a.model.a = a.model.r / 2.0;
-      a.model.gnorm = 2.0 / std::tgamma(a.model.s);
-      break;
-    default: a.model.a = a.model.r / std::pow(3.0, 1.0 / a.model.s); break;
-  }
-  a.model.lut = matrix_lut;
-  a.model.lut_size = lut_size;
-  a.model.lut_range = model_params[4];
-  a.model.lut_out = model_params[5];
+  a.sample_cov = sample_cov;
   a.radius = radius; a.min_points = min_points; a.max_points = max_points;
   a.z = z; a.sigma = sigma; a.status = status; a.t0 = target_begin; a.t1 = target_end;
   a.exclude = exclude;
   if (target_end == target_begin) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int smem_budget = 226 * 1024;
+  const int smem_budget = 227 * 1024;  // the opt-in maximum of dynamic shared memory per CTA
   const int64_t ntarget = target_end - target_begin;
   // pass 1: covariance-form Cholesky (fast path)
   {
     KrigeArgs c = a;
     int per_warp = 0;
-    krige_chol_layout(max_points, dim, &c.cap, &c.region_bytes, &per_warp);
-    const int wpb = best_wpb(per_warp, smem_budget);
+    krige_chol_layout(max_points, dim, sample_cov != nullptr, &c.cap, &c.region_bytes, &per_warp);
+    const int wpb = best_wpb(per_warp, smem_budget, 16);
     if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
     const size_t smem = (size_t)wpb * per_warp;
     auto kern = dim == 3 ? krige_chol_kernel<3> : krige_chol_kernel<2>;
@@ -1070,7 +1155,7 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
     int per_warp = 0;
     krige_layout(max_points, dim, &a.cap, &a.region_bytes, &per_warp);
     a.retry_only = 1;
-    const int wpb = best_wpb(per_warp, smem_budget);
+    const int wpb = best_wpb(per_warp, smem_budget, 8);
     if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
     const size_t smem = (size_t)wpb * per_warp;
     auto kern = dim == 3 ? krige_kernel<3> : krige_kernel<2>;

@@ -62,8 +62,9 @@ SIGNATURES = {
                                     _i64, _i64, _p]),
     "skg_krige_build_grid": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p]),
     "skg_krige_scratch_bytes": (_i64, [_int]),
+    "skg_krige_sample_cov": (_int, [_p, _i64, _int, _int, _p, _p, _int, _p, _p]),
     "skg_krige": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _i64, _int, _p, _p, _int, _dbl, _int, _int,
-                         _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
+                         _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
 }
 
 _lib = None

@@ -1383,6 +1383,28 @@ class KrigeEngine:
         _lib.check(rc, "skg_krige_build_grid")
         self.launches += 4
         self._scratch = torch.empty(16, dtype=torch.uint8, device=self.device)
+        self._cov, self._cov_key = None, None
+
+    SAMPLE_COV_MAX_BYTES = 4 << 30   # cache the N x N sample covariance up to this size (N <= 23170)
+
+    def _sample_cov(self, model, mp, matrix_lut):
+        """c_t - gamma(d_ij) of all sample pairs on the device (skg_krige_sample_cov), built once per
+        (model, parameters) and reused by every transform: the per-target matrix build becomes a
+        gather.  None when N x N doubles exceed SAMPLE_COV_MAX_BYTES (computed on the fly then)."""
+        if self.n * self.n * 8 > self.SAMPLE_COV_MAX_BYTES:
+            return None
+        key = (model, tuple(float(x) for x in mp), None if matrix_lut is None else int(matrix_lut.data_ptr()))
+        if self._cov_key != key:
+            if self._cov is None:
+                self._cov = torch.empty(self.n * self.n, dtype=torch.float64, device=self.device)
+            rc = self.lib.skg_krige_sample_cov(
+                _ptr(self.coords), self.n, self.dim, _lib.MODEL_IDS[model], _hptr(np.ascontiguousarray(mp)),
+                _ptr(matrix_lut), 0 if matrix_lut is None else int(matrix_lut.numel()), _ptr(self._cov),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            _lib.check(rc, "skg_krige_sample_cov")
+            self.launches += 1
+            self._cov_key = key
+        return self._cov
 
     @classmethod
     def _grid_params(cls, c, radius):
@@ -1460,7 +1482,8 @@ class KrigeEngine:
             _ptr(self.cell_start), _ptr(self.order), _ptr(targets_soa), m,
             _lib.MODEL_IDS[model], _hptr(mp), _ptr(matrix_lut),
             0 if matrix_lut is None else int(matrix_lut.numel()), self.radius, int(min_points), int(max_points),
-            _ptr(exclude), _ptr(z), _ptr(sigma), _ptr(status), _ptr(self._scratch), self._scratch.numel(),
+            _ptr(exclude), _ptr(self._sample_cov(model, mp, matrix_lut)), _ptr(z), _ptr(sigma), _ptr(status),
+            _ptr(self._scratch), self._scratch.numel(),
             b, e, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         _lib.check(rc, "skg_krige")
         self.launches += 2 if e > b else 0

@@ -56,7 +56,7 @@ def test_argument_errors_do_not_need_a_gpu():
                                   None, 0, 0, None)
     assert rc == -2 and b"dim" in lib.skg_last_error()
     rc = lib.skg_krige(None, None, 0, 2, None, None, None, None, 0, 0, None, None, 0, 1.0, 1, 1, None, None,
-                       None, None, None, 0, 0, 0, None)
+                       None, None, None, None, 0, 0, 0, None)
     assert rc == -1
     with pytest.raises(_lib.SkgError):
         _lib.check(rc, "skg_krige")
