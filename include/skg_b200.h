@@ -48,7 +48,7 @@ extern "C" {
 #define SKG_ABI_VERSION 5
 #define SKG_TILE 256            /* points per tile edge                          */
 #define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
-#define SKG_KRIGE_MAX_POINTS 64 /* max_points supported by the warp-per-target kernel */
+#define SKG_KRIGE_MAX_POINTS 128 /* max_points supported by the warp-per-target kernels (<= 64: the fast layout) */
 
 /* error codes (<0) */
 #define SKG_E_BADARG (-1)

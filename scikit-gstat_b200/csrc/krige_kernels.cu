@@ -459,7 +459,7 @@ __device__ __forceinline__ int find_neighbours(const KrigeArgs& a, double tx, do
     return len;
 }
 
-template <int DIM>
+template <int DIM, int NQ>  // NQ: neighbour slots per lane (max_points <= 32 * NQ)
 __global__ void __launch_bounds__(256)
 krige_kernel(const __grid_constant__ KrigeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -504,10 +504,10 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
       continue;
     }
     // pull the neighbours out of the list region before it becomes the matrix
-    double kd[2];
-    int kid[2];
+    double kd[NQ];
+    int kid[NQ];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int e = lane + 32 * q;
       kd[q] = e < nn ? __longlong_as_double((long long)keys[e]) : 0.0;
       kid[q] = e < nn ? ids[e] : 0;
@@ -516,7 +516,7 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
     const int N = nn + 1;   // system size
     const int LD = (N + 1) | 1;  // augmented with the rhs column (index N); odd stride keeps column walks bank-conflict free
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int e = lane + 32 * q;
       if (e < nn) {
         ncoord[e] = X[kid[q]];
@@ -605,7 +605,7 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
       // that exist) and walks the rows in batches of 4: all loads of a batch are issued
       // before its FMAs/stores, so the shared-memory latency is paid once per batch, not
       // once per element.
-      {
+      if (NQ == 2) {
         const int NC = N + 1;  // real columns (rhs included); padding columns are skipped
         const int j0 = k + 1 + lane;
         const bool c0 = j0 < NC, c1 = j0 + 32 < NC, c2 = j0 + 64 < NC;
@@ -633,6 +633,13 @@ krige_kernel(const __grid_constant__ KrigeArgs a) {
               }
             }
           }
+        }
+      } else {
+        // wide systems (max_points > 64): any number of column slots per lane
+        const int NC = N + 1;
+        for (int j = k + 1 + lane; j < NC; j += 32) {
+          const double u = A[k * LD + j];
+          for (int i = k + 1; i < N; ++i) A[i * LD + j] = fma(-mult[i], u, A[i * LD + j]);
         }
       }
       __syncwarp();
@@ -689,8 +696,8 @@ __device__ __forceinline__ int prow(int i, int n) {  // offset of packed row i (
   return i <= n ? i * (i + 1) / 2 : n * (n + 1) / 2 + n;
 }
 
-template <int DIM>
-__global__ void __maxnreg__(104)
+template <int DIM, int NQ>  // NQ: neighbour slots per lane (max_points <= 32 * NQ)
+__global__ void __maxnreg__(NQ == 2 ? 104 : 128)
 krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -732,10 +739,10 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
       __syncwarp();
       continue;
     }
-    double kd[2];
-    int kid[2];
+    double kd[NQ];
+    int kid[NQ];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int e = lane + 32 * q;
       kd[q] = e < nn ? __longlong_as_double((long long)keys[e]) : 0.0;
       kid[q] = e < nn ? ids[e] : 0;
@@ -744,7 +751,7 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     const int n = nn;
     const int rowc = prow(n, n), rowo = prow(n + 1, n);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int e = lane + 32 * q;
       if (e < n) {
         if (!cached) {
@@ -912,18 +919,41 @@ krige_chol_kernel(const __grid_constant__ KrigeArgs a) {
     const double mu = (1.0 - s12) / s11;
     // back substitution L' w = y1 + mu y2 in axpy form: y lives in registers (lane owns
     // entries lane and lane+32), row i of L is read contiguously, no reductions
-    double yA = lane < n ? fma(mu, L[rowo + lane], L[rowc + lane]) : 0.0;
-    double yB = lane + 32 < n ? fma(mu, L[rowo + lane + 32], L[rowc + lane + 32]) : 0.0;
-    for (int i = n - 1; i >= 0; --i) {
-      const int oi = i * (i + 1) / 2;
-      const double yi = __shfl_sync(0xffffffffu, i < 32 ? yA : yB, i & 31);
-      const double wi = yi / L[oi + i];
-      if (lane == (i & 31)) { if (i < 32) yA = wi; else yB = wi; }
-      if (lane < i) yA = fma(-L[oi + lane], wi, yA);
-      if (lane + 32 < i) yB = fma(-L[oi + lane + 32], wi, yB);
+    if (NQ == 2) {
+      double yA = lane < n ? fma(mu, L[rowo + lane], L[rowc + lane]) : 0.0;
+      double yB = lane + 32 < n ? fma(mu, L[rowo + lane + 32], L[rowc + lane + 32]) : 0.0;
+      for (int i = n - 1; i >= 0; --i) {
+        const int oi = i * (i + 1) / 2;
+        const double yi = __shfl_sync(0xffffffffu, i < 32 ? yA : yB, i & 31);
+        const double wi = yi / L[oi + i];
+        if (lane == (i & 31)) { if (i < 32) yA = wi; else yB = wi; }
+        if (lane < i) yA = fma(-L[oi + lane], wi, yA);
+        if (lane + 32 < i) yB = fma(-L[oi + lane + 32], wi, yB);
+      }
+      if (lane < n) xv[lane] = yA;
+      if (lane + 32 < n) xv[lane + 32] = yB;
+    } else {
+      double y[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        y[q] = lane + 32 * q < n ? fma(mu, L[rowo + lane + 32 * q], L[rowc + lane + 32 * q]) : 0.0;
+      for (int i = n - 1; i >= 0; --i) {
+        const int oi = i * (i + 1) / 2;
+        double ysrc = y[0];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) ysrc = (i >> 5) == q ? y[q] : ysrc;
+        const double yi = __shfl_sync(0xffffffffu, ysrc, i & 31);
+        const double wi = yi / L[oi + i];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          if (lane == (i & 31) && (i >> 5) == q) y[q] = wi;
+          if (lane + 32 * q < i) y[q] = fma(-L[oi + lane + 32 * q], wi, y[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (lane + 32 * q < n) xv[lane + 32 * q] = y[q];
     }
-    if (lane < n) xv[lane] = yA;
-    if (lane + 32 < n) xv[lane + 32] = yB;
     __syncwarp();
     double sz = 0.0, ss = 0.0;
     for (int i = lane; i < n; i += 32) {
@@ -1141,7 +1171,8 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
     const int wpb = best_wpb(per_warp, smem_budget, 16);
     if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
     const size_t smem = (size_t)wpb * per_warp;
-    auto kern = dim == 3 ? krige_chol_kernel<3> : krige_chol_kernel<2>;
+    auto kern = max_points <= 64 ? (dim == 3 ? krige_chol_kernel<3, 2> : krige_chol_kernel<2, 2>)
+                                 : (dim == 3 ? krige_chol_kernel<3, 4> : krige_chol_kernel<2, 4>);
     SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
@@ -1158,7 +1189,8 @@ int skg_krige(const double* coords, const double* values, int64_t n, int dim, co
     const int wpb = best_wpb(per_warp, smem_budget, 8);
     if (wpb < 1) { set_error("max_points=%d does not fit shared memory", max_points); return SKG_E_UNSUPPORTED; }
     const size_t smem = (size_t)wpb * per_warp;
-    auto kern = dim == 3 ? krige_kernel<3> : krige_kernel<2>;
+    auto kern = max_points <= 64 ? (dim == 3 ? krige_kernel<3, 2> : krige_kernel<2, 2>)
+                                 : (dim == 3 ? krige_kernel<3, 4> : krige_kernel<2, 4>);
     SKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));

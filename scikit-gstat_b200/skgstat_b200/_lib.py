@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SKG_B200_LIB") or os.path.join(_HERE, "libskg_b200.so
 ABI_VERSION = 5
 TILE = 256
 MAX_LAGS = 250
-KRIGE_MAX_POINTS = 64
+KRIGE_MAX_POINTS = 128
 
 DIR_NONE, DIR_TRIANGLE, DIR_COMPASS = 0, 1, 2
 STAT_SUM_SQ, STAT_SUM_SQRT, STAT_COUNT_BELOW = 1, 2, 4

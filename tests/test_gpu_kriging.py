@@ -86,6 +86,28 @@ def test_kriging_against_oracle(skg, model, shape, maxp):
     assert_allclose(ok.sigma, sr, rtol=1e-9, atol=4e-9, equal_nan=True)
 
 
+@pytest.mark.parametrize("maxp,rad", [(65, 200.0), (100, 250.0), (128, 300.0)])
+def test_kriging_wide_neighbourhoods_against_oracle(skg, maxp, rad):
+    """max_points beyond 64: the 4-slots-per-lane variants of both solvers.  The
+    reference has no limit (Kriging.py:145-158, 305-330); 128 is this library's."""
+    c = random_points(2500, 1000.0, 2, seed=18)
+    v = gaussian_field(c, 100.0, seed=18)
+    rng = np.random.default_rng(maxp)
+    t = rng.random((150, 2)) * 1200.0 - 100.0
+    t[:10] = c[:10]
+    zr, sr, st = okr.krige(c, v, t, "exponential", rad, 4.0, 0.3, None, 5, maxp)
+    d = dict(model="exponential", effective_range=rad, sill=4.0, nugget=0.3, dist_func="euclidean")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ok = skg.OrdinaryKriging(d, min_points=5, max_points=maxp, coordinates=c, values=v)
+        z = ok.transform(t[:, 0], t[:, 1])
+    assert_array_equal(np.isnan(z), np.isnan(zr))
+    assert_allclose(z, zr, rtol=1e-9, equal_nan=True)
+    assert_allclose(ok.sigma, sr, rtol=1e-9, atol=4e-9, equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        skg.OrdinaryKriging(d, min_points=5, max_points=129, coordinates=c, values=v).transform(t[:, 0], t[:, 1])
+
+
 def test_kriging_ties_on_lattice_and_duplicates(skg):
     gx, gy = np.meshgrid(np.arange(30.0), np.arange(30.0))
     c = np.column_stack((gx.ravel(), gy.ravel()))
