@@ -246,7 +246,10 @@ int skg_pair_select_hist(const double* coords, const double* values, int n_value
  * (np.median / np.percentile / np.nanpercentile over the distance vector, Variogram.py:1288-1293,
  * binning.py:70-79, DirectionalVariogram.py:509); the cell holding a wanted rank is narrow enough
  * to be gathered (skg_pair_select_gather) or refined with nearly every tile culled.
- *   count [dev, SKG_CELL_COUNT] += pairs per cell;  scratch >= skg_pair_cell_scratch_bytes(n). */
+ *   count [dev, SKG_CELL_COUNT] += pairs per cell;  scratch >= skg_pair_cell_scratch_bytes(n).
+ * With a directional mask under policy dir[4] = 1 the sweep also counts the guard-band pairs it
+ * meets (any distance inside the swept tiles) in the 7th uint64 of `scratch`: zero after a sweep
+ * over the full distance range means skg_pair_dir_ambiguous has nothing to list. */
 #define SKG_CELL_COUNT 4096
 int64_t skg_pair_cell_scratch_bytes(int64_t n);
 int skg_pair_cell_counts(const double* coords, int64_t n, int dim, const double* dir,

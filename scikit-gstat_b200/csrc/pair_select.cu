@@ -56,7 +56,8 @@ pair_cellcount_kernel(const double* __restrict__ coords, int64_t n,
                       unsigned long long hi_bits, int shift, int key0,
                       unsigned long long* __restrict__ count, const unsigned int* __restrict__ tile_list,
                       const unsigned long long* __restrict__ tile_count,
-                      const double* __restrict__ bbox32, double wlo, double whi, int js) {
+                      const double* __restrict__ bbox32, double wlo, double whi, int js,
+                      unsigned long long* __restrict__ amb_count) {
   __shared__ double2 sXY[TILE];
   __shared__ double sW[DIM == 3 ? TILE : 1];
   __shared__ unsigned int sCnt[CELLS];
@@ -70,6 +71,7 @@ pair_cellcount_kernel(const double* __restrict__ coords, int64_t n,
   const double* __restrict__ W = coords + 2 * n;
   const int jchunk = TILE / js;
   const int64_t nwork = (int64_t)(*tile_count);
+  unsigned int namb = 0u;  // guard-band pairs seen (DIR == 1: they are excluded here and resolved by the caller)
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const unsigned int item = tile_list[w];
     const int64_t t = item / (unsigned)js;
@@ -126,7 +128,14 @@ pair_cellcount_kernel(const double* __restrict__ coords, int64_t n,
         const unsigned long long sb = (unsigned long long)__double_as_longlong(s);
         bool in = sb >= lo_bits && sb < hi_bits;             // NaN bit patterns lie above hi_bits
         if (diag) in = in && (jbeg + jj > r * HB + tid);     // keep i < j only
-        if (DIR) in = in && dir_mask_t<DIR == 2>(dx, dy, s, dp);
+        if (DIR == 1) {
+          bool amb = false;
+          const bool ok = (s > 0.0) && dir_fast(dx, dy, dp, &amb);
+          if (amb && s > 0.0 && (!diag || jbeg + jj > r * HB + tid)) ++namb;
+          in = in && ok && !amb;
+        } else if (DIR) {
+          in = in && dir_mask_t<true>(dx, dy, s, dp);
+        }
         if (in) {
           const int c = (int)((unsigned)(sb >> 32) >> shift) - key0;
           atomicAdd(&sCnt[min(max(c, 0), CELLS - 1)], 1u);
@@ -141,6 +150,7 @@ pair_cellcount_kernel(const double* __restrict__ coords, int64_t n,
     const unsigned int v = sCnt[k];
     if (v) atomicAdd(&count[k], (unsigned long long)v);
   }
+  if (DIR == 1 && namb) atomicAdd(amb_count, (unsigned long long)namb);
 }
 
 template <int DIM, int DIR>
@@ -155,7 +165,7 @@ static int launch_cellcount(const double* coords, int64_t n, const DirParams& dp
   int64_t grid = (int64_t)sm_count() * occ;
   if (grid > ntiles * js) grid = ntiles * js;
   kern<<<(unsigned)grid, HB, 0, st>>>(coords, n, dp, lo_bits, hi_bits, shift, key0, count, S.list,
-                                      S.counters, S.bbox32, wlo, whi, js);
+                                      S.counters, S.bbox32, wlo, whi, js, S.counters + 6);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

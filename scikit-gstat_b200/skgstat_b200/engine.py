@@ -709,6 +709,15 @@ class PairEngine:
                 self._stream())
         _lib.check(rc, "skg_pair_cell_counts")
         self.launches += 5 if self.t1 > self.t0 else 0
+        if dirp is not None and dirp[4] != 0.0 and lo_bits == 0 and hi_bits > to_bits(self.sq_upper_bound()) \
+                and self.pair_filter is None:
+            # the sweep met every pair the mask can pass: no guard-band pair seen (on any rank) means
+            # there is none, and the listing sweep (skg_pair_dir_ambiguous) is not needed at all
+            seen = int(scratch[:64].view(torch.int64)[6].item())
+            if D.allreduce_max_int(seen, self.device, self.group) == 0:
+                empty = (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))
+                for tiles in ((self.t0, self.t1, self.tstride), (0, self.n_tiles, 1)):
+                    self._amb_cache.setdefault(tuple(float(x) for x in dirp) + tiles, empty)
         amb = self.ambiguous_pairs(dirp)
         if amb is not None and amb[0].size:
             s_bits, _ = self._amb_keys(amb)
