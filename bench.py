@@ -55,8 +55,15 @@ HEADLINE = ("2-D synthetic Gaussian field N=200000 (19999900000 pairs), cressie,
             "maxlag=median (BASELINE.json config 3)")
 # from the committed ncu --set full captures of the dominant kernels (profiles/)
 NCU = {
-    "pair_hist_win": {"fp64_pipe_pct": 58.8, "traffic_bytes": 6708992,
-                      "from": "profiles/r2_pair_hist_win_ncu_summary.txt (N=200k, matheron)"},
+    "cressie": {"fp64_pipe_pct": 63.9, "issue_active_pct": 59.8, "smem_wavefronts_pct": 21.4,
+                "traffic_bytes": 6699264,
+                "from": "profiles/r2_pair_hist_win_cressie_ncu_summary.txt (N=200k, 15.80 ms under ncu)"},
+    "matheron": {"fp64_pipe_pct": 58.7, "issue_active_pct": 61.4, "smem_wavefronts_pct": 30.7,
+                 "traffic_bytes": 6692352,
+                 "from": "profiles/r2_pair_hist_win_ncu_summary.txt (N=200k, 11.07 ms under ncu)"},
+    "kriging": {"fp64_pipe_pct": 6.3, "issue_active_pct": 40.5, "smem_wavefronts_pct": 49.4,
+                "traffic_bytes": 245.0e6,
+                "from": "profiles/r2_krige_chol_ncu_summary.txt (400x400 targets, 9.21 ms under ncu)"},
 }
 
 
@@ -319,8 +326,12 @@ def roofline(X, flops_per_pair, pairs_rank, info, kern_ms, kernel, ncu=None):
            "peak_source": "DFMA chain measured in this run (skg_fp64_peak); MEASURED_PEAKS.json has no "
                           "FP64 figure"}
     if ncu:
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this
+        # configuration, from the committed capture named in ncu_from
         out["traffic"] = ncu["traffic_bytes"]
         out["fp64_pipe_pct"] = ncu["fp64_pipe_pct"]
+        out["issue_active_pct"] = ncu["issue_active_pct"]
+        out["smem_wavefronts_pct"] = ncu["smem_wavefronts_pct"]
         out["ncu_from"] = ncu["from"]
     return out
 
@@ -399,7 +410,7 @@ def run_own(args):
                     "call": "Variogram(coords, values, 'cressie', n_lags=25, maxlag='median').experimental"},
             "gpu_launches": int(launches),
             "roofline": roofline(X, FLOPS["cressie"], pairs3 / world, info, kern_ms,
-                                 "pair_hist_win_kernel<2,1> (cressie: sum sqrt|dz|)", NCU["pair_hist_win"]),
+                                 "pair_hist_win_kernel<2,1> (cressie: sum sqrt|dz|)", NCU["cressie"]),
         }
         out["roofline"]["hbm"] = {"algorithmic_bytes": 8.0 * 3 * n3 + 24.0 * N_LAGS,
                                   "achieved_gbs": (8.0 * 3 * n3 + 24.0 * N_LAGS) / (kern_ms * 1e-3) / 1e9}
@@ -418,7 +429,7 @@ def run_own(args):
             "value": pairs3 / (sm * 1e-3), "unit": UNIT, "ms_per_step": sm,
             "e2e": {"value": pairs3 / em_s, "unit": UNIT, "ms_per_step": em_s * 1e3},
             "roofline": roofline(X, FLOPS["matheron"], pairs3 / world, info_m, km,
-                                 "pair_hist_win_kernel<1,1> (matheron: sum dz^2)", NCU["pair_hist_win"])}
+                                 "pair_hist_win_kernel<1,1> (matheron: sum dz^2)", NCU["matheron"])}
         out["config3_dowd"] = {
             "e2e": {"value": pairs3 / ed_s, "unit": UNIT, "ms_per_step": ed_s * 1e3,
                     "h2d_bytes_per_step": int(dh2d), "d2h_bytes_per_step": int(dd2h),
@@ -562,7 +573,12 @@ def bench_kriging(skg, args, X, world, rank):
                         "achieved_counting_reference_lu": 2.6e5 * m / (ms * 1e-3) / 1e12,
                         "note": "the kernel solves the covariance form by Cholesky (about 1/2 of the "
                                 "reference's LU flops); `achieved`/`frac` count the executed formulation",
-                        "kernel": "krige_chol_kernel<2>", "kernel_ms": ms}}
+                        "kernel": "krige_chol_kernel<2,2>", "kernel_ms": ms,
+                        "traffic": NCU["kriging"]["traffic_bytes"] * m / 160000.0,
+                        "fp64_pipe_pct": NCU["kriging"]["fp64_pipe_pct"],
+                        "issue_active_pct": NCU["kriging"]["issue_active_pct"],
+                        "smem_wavefronts_pct": NCU["kriging"]["smem_wavefronts_pct"],
+                        "ncu_from": NCU["kriging"]["from"] + "; traffic scaled by the target count"}}
     if world == 1:
         ok.transform(gx, gy)   # warm-up of the public call (pinned staging buffers are allocated once)
         Traffic.reset()

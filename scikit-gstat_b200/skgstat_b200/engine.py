@@ -614,6 +614,12 @@ class PairEngine:
             keys = self._buffer("gather_keys", max(cap, 1), torch.float64)
             slots = self._buffer("gather_slots", max(cap, 1), torch.int32)
             cnt = self._buffer("gather_cnt", 1, torch.int64).zero_()
+            # single rank, ranks picked on the device: no host round trip for the candidate count -
+            # unwritten entries keep slot -1, which no wanted slot matches, and exact_select checks
+            # the per-slot counts that come back with the picks
+            nosync = self.world == 1 and want is not None and not (amb_key is not None and amb_key.size)
+            if nosync:
+                slots.fill_(-1)
             bm = to_device(bitmap.view(np.int32), self.device)
             lo = np.ascontiguousarray(lo, dtype=np.uint64)
             hi = np.ascontiguousarray(hi, dtype=np.uint64)
@@ -626,11 +632,12 @@ class PairEngine:
                     scratch.numel(), self.t0, self.t1, self.tstride, self._stream())
             _lib.check(rc, "skg_pair_select_gather")
             self.launches += 4 if self.t1 > self.t0 else 0
-            got = int(cnt.item())
-            worst = got if self.world == 1 else D.allreduce_max_int(got, self.device, self.group)
-            if worst > cap:   # decided collectively, so every rank raises (no rank is left in a collective)
-                raise RuntimeError("gather overflow: %d > %d" % (worst, cap))
-            keys, slots = keys[:got], slots[:got]
+            if not nosync:
+                got = int(cnt.item())
+                worst = got if self.world == 1 else D.allreduce_max_int(got, self.device, self.group)
+                if worst > cap:   # decided collectively, so every rank raises (no rank is left in a collective)
+                    raise RuntimeError("gather overflow: %d > %d" % (worst, cap))
+                keys, slots = keys[:got], slots[:got]
             if amb_key is not None and amb_key.size:
                 k, sl = amb_slots(lo, hi, sc)
                 hit = ((bitmap[sl >> 5] >> (sl & 31).astype(np.uint32)) & 1).astype(bool)
