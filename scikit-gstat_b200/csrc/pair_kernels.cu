@@ -780,7 +780,25 @@ static int select_common(bool gather, const double* coords, const double* values
   const int use_dir = dp.model == SKG_DIR_NONE ? 0 : (dp.amb_exclude ? 1 : 2);
   SelectLaunch L{coords, values, n, &tab, &dp, &host_seg, n_buckets, hist, max_bits, bitmap,
                  cand_key, cand_slot, cand_count, capacity, ntiles, S.list, S.counters, S.bbox,
-                 S.bbox32, wlo, whi, js, st, mv, getenv("SKG_GROUP_CULL_OFF") ? nullptr : S.bbox8};
+                 S.bbox32, wlo, whi, js, st, mv, getenv("SKG_GROUP_CULL_OFF") ? nullptr : S.bbox8, -1, 0.0, 0.0};
+  if (key_kind == SKG_KEY_SQDIST && !use_mv && getenv("SKG_FAST_SEG_OFF") == nullptr) {
+    // exactly one segment with a window, lying inside that segment's class (or no classes at all):
+    // membership is lo <= s < hi, no lag-class lookup needed
+    int only = -1, cnt = 0;
+    for (int k = 0; k < nseg; ++k)
+      if (seg_hi_bits[k] > seg_lo_bits[k]) { only = k; ++cnt; }
+    if (cnt == 1 && seg_hi_bits[only] <= INF_BITS + 1) {
+      const uint64_t c_lo = (n_lags > 0 && only > 0) ? thr_bits[only - 1] : 0ull;
+      const uint64_t c_hi = n_lags > 0 ? thr_bits[only] : INF_BITS + 1;
+      const uint64_t lo = std::max(seg_lo_bits[only], c_lo), hi = std::min(seg_hi_bits[only], c_hi);
+      if (hi > lo && !(n_lags <= 0 && max_bits != nullptr && !gather)) {
+        L.fast_seg = only;
+        L.fast_lo = bits_to_double(lo);
+        L.fast_hi = hi > INF_BITS ? bits_to_double(INF_BITS) : bits_to_double(hi);
+        if (hi > INF_BITS) L.fast_seg = -1;  // an unbounded window keeps the general path (s = +inf)
+      }
+    }
+  }
   rc = use_mv ? dispatch_select_mv(gather, dim, use_dir, L)
               : dispatch_select(gather, dim, use_dir, n_lags > 0, key_kind, L);
   return rc;

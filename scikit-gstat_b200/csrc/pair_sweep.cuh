@@ -600,7 +600,11 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
                    long long capacity, const unsigned int* __restrict__ tile_list,
                    const unsigned long long* __restrict__ tile_count,
                    const double* __restrict__ bbox, const double* __restrict__ bbox32, double wlo,
-                   double whi, int js, const MvSpec mv, const double* __restrict__ bbox8) {
+                   double whi, int js, const MvSpec mv, const double* __restrict__ bbox8,
+                   int fast_seg, double fast_lo, double fast_hi) {
+  // fast_seg >= 0 (distance keys, exactly ONE segment with a window, e.g. the gather of a median):
+  // a pair belongs to segment fast_seg iff fast_lo <= s < fast_hi, everything else is skipped without
+  // the lag-class lookup - the sweep then costs the distance and two compares per pair
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sW[DIM == 3 ? TILE + 2 : 1];
   __shared__ double sZ[TILE + 2];
@@ -766,7 +770,8 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
           }
           const uint64_t sb = (uint64_t)__double_as_longlong(s);
           int gg;
-          if (SEG) gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
+          if (KEY == SKG_KEY_SQDIST && fast_seg >= 0) gg = (s >= fast_lo && s < fast_hi) ? fast_seg : nb;
+          else if (SEG) gg = lag_of<EMAX>(sb, sThr, lutb, shift, klo, khi, emax);
           else gg = sb <= INF_BITS ? 0 : nb;  // NaN: padded point or NaN coordinate
           if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
           if (DIR) {
@@ -778,6 +783,12 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
         }
       };
       auto accumulate = [&](const int (&g)[HR], const double (&key)[HR]) {
+        if (KEY == SKG_KEY_SQDIST && fast_seg >= 0) {  // hits are rare: skip the whole step when the warp has none
+          bool any = false;
+#pragma unroll
+          for (int r = 0; r < HR; ++r) any |= g[r] < nb;
+          if (!__any_sync(0xffffffffu, any)) return;
+        }
         // window test for all HR pairs first, branch-free (most in-range keys lie outside the
         // windows: only the few that hit take the bucket / atomic path below)
         bool inw[HR];
@@ -903,6 +914,7 @@ struct SelectLaunch {
   const double* bbox; const double* bbox32; double wlo, whi; int js; cudaStream_t st;
   MvSpec mv;
   const double* bbox8;
+  int fast_seg; double fast_lo, fast_hi;  // single-window distance select (see pair_select_kernel)
 };
 
 template <int DIM, int DIR, bool SEG, int KEY, bool GATHER, int EMAX, bool VM>
@@ -918,7 +930,8 @@ static int launch_select(const SelectLaunch& L) {
       L.coords, L.values, L.n, *L.tab, *L.dp, *L.seg, (long long)L.nbuckets,
       reinterpret_cast<unsigned long long*>(L.hist), reinterpret_cast<unsigned long long*>(L.max_bits),
       L.bitmap, L.cand_key, L.cand_slot, reinterpret_cast<unsigned long long*>(L.cand_count),
-      (long long)L.capacity, L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi, L.js, L.mv, L.bbox8);
+      (long long)L.capacity, L.list, L.list_count, L.bbox, L.bbox32, L.wlo, L.whi, L.js, L.mv, L.bbox8,
+      L.fast_seg, L.fast_lo, L.fast_hi);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

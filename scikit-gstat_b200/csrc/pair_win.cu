@@ -549,7 +549,8 @@ int dispatch_hist_win(int emax, int stats, const HistLaunch& L) {
     if (stats == 2) return launch_hist_win_t<2, 1>(L);
     return launch_hist_win_t<3, 1>(L);
   }
-  if (stats == 0) return launch_hist_win_t<0, 0>(L);
+  if (stats == 0) return emax == 2 ? launch_hist_win_t<0, 2>(L) : launch_hist_win_t<0, 0>(L);  // count sweeps of the
+  // select cluster their thresholds: two per table cell is common there
   if (stats == 1) return launch_hist_win_t<1, 0>(L);
   if (stats == 2) return launch_hist_win_t<2, 0>(L);
   return launch_hist_win_t<3, 0>(L);

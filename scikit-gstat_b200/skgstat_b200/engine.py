@@ -857,6 +857,7 @@ class PairEngine:
         cum = np.cumsum(counts)
         lows = np.concatenate((np.zeros(1, dtype=np.uint64), thr[:-1]))   # (a Python 0 would promote to float64)
         bands = {}   # window class -> thresholds strictly inside it
+        centres = {}  # window class -> relative positions already banded (adjacent ranks share one band)
         for r in ranks:
             c = int(np.searchsorted(cum, r, side="right"))
             n_in = int(counts[c])
@@ -866,12 +867,19 @@ class PairEngine:
             if not (np.isfinite(lo_v) and np.isfinite(hi_v) and hi_v > lo_v):
                 continue
             rel = (r - (int(cum[c - 1]) if c else 0) + 0.5) / n_in
-            frac_cell = min(0.25, self.REFINE_CELL_KEYS / n_in)       # mass of one refinement cell
+            # cells of ~REFINE_CELL_KEYS keys, but a band of at least -/+ 2 % of the window's keys: the
+            # interpolation (linear in the DISTANCE, whose density is the smoother one) is good to ~1 %
+            frac_cell = min(0.25, max(self.REFINE_CELL_KEYS / n_in, 0.04 / self.REFINE_CELLS))
+            if any(abs(rel - x) < 0.25 * frac_cell for x in centres.get(c, [])):
+                continue
+            centres.setdefault(c, []).append(rel)
             half = self.REFINE_CELLS // 2
+            d_lo, d_hi = np.sqrt(lo_v), np.sqrt(hi_v)
             for k in range(-half, half + 1):
                 f = rel + k * frac_cell
                 if 0.0 < f < 1.0:
-                    t = to_bits(lo_v + (hi_v - lo_v) * f)
+                    dd = d_lo + (d_hi - d_lo) * f
+                    t = to_bits(float(dd * dd))
                     if int(lows[c]) < t < int(thr[c]):
                         bands.setdefault(c, set()).add(t)
         if not bands:
@@ -891,6 +899,13 @@ class PairEngine:
             c2 = c2[1:] if int(lows[c]) > 0 else c2          # drop the class below the window
             if int(c2.sum()) != int(counts[c]):
                 raise RuntimeError("window refinement count mismatch: %d != %d" % (int(c2.sum()), int(counts[c])))
+            if _DEBUG_TIMES:
+                cc = np.cumsum(c2)
+                for r in ranks:
+                    rr = r - (int(cum[c - 1]) if c else 0)
+                    print("   [interp] rank at %.4f of the window, predicted cell %d of %d, found in cell %d; keys per cell ~%d, window keys %d"
+                          % (rr / max(int(counts[c]), 1), len(inner) // 2, len(c2), int(np.searchsorted(cc, rr, side="right")),
+                             int(np.median(c2[1:-1])) if len(c2) > 2 else 0, int(counts[c])))
             out_thr += inner + [int(thr[c])]
             out_cnt += [int(x) for x in c2]
         return np.array(out_thr, dtype=np.uint64), np.array(out_cnt, dtype=np.int64)
