@@ -820,7 +820,7 @@ int64_t skg_pair_scratch_bytes(int64_t n, int n_lags) {
   if (n_lags < 1) n_lags = 1;
   if (n < 0) n = 0;
   return sweep_head_bytes(n) +
-         (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial);
+         (int64_t)sm_count() * MAX_GRID_PER_SM * n_lags * (int64_t)sizeof(HistPartial) + (int64_t)sizeof(DzTable) + 256;
 }
 
 static int pair_hist_impl(const double* coords, const double* values, int n_values, int value_mode,
@@ -884,17 +884,26 @@ static int pair_hist_impl(const double* coords, const double* values, int n_valu
     }
   HistLaunch L{coords, values, n, &tab, &dp, partial, S.list, S.counters, S.bbox, S.bbox32,
                win.lo[0], win.hi[0], &dzt, max_blocks, ntl, js, 0, st, &nblocks, mv, S.bbox8,
-               reinterpret_cast<unsigned long long*>(whist), (long long)n_buckets};
+               reinterpret_cast<unsigned long long*>(whist), (long long)n_buckets, nullptr};
   // register lag windows: 2-D isotropic sweeps over scalar values with an estimator sum
   const bool win_off = getenv("SKG_WIN_OFF") != nullptr;  // developer switch: first kernel only
-  if (!win_off && dim == 2 && dp.model == SKG_DIR_NONE && !use_mv && stats >= 0 && stats <= 3) {
+  if (!win_off && dim == 2 && dp.model == SKG_DIR_NONE && !use_mv && stats >= 0 && stats <= 4 &&
+      !(stats == 4 && S.tail_bytes < (int64_t)max_blocks * n_lags * (int64_t)sizeof(HistPartial) + (int64_t)sizeof(DzTable))) {
     L.smem = hist_win_smem_bytes(n_lags, stats);
     if (L.smem <= 160 * 1024) {
+      if (stats == 4) {
+        // the |dz| window table travels through the scratch tail (6 KB: too large next to the lag
+        // table for the kernel-parameter space); stream-ordered copy from the caller-visible struct
+        unsigned char* dst = S.tail + (int64_t)max_blocks * n_lags * (int64_t)sizeof(HistPartial);
+        SKG_CUDA(cudaMemcpyAsync(dst, &dzt, sizeof(DzTable), cudaMemcpyHostToDevice, st));
+        L.dzt_dev = reinterpret_cast<const DzTable*>(dst);
+      }
       rc = dispatch_hist_win(tab.emax, stats, L);
       if (rc) return rc;
       pair_hist_reduce_kernel<<<n_lags, 32, 0, st>>>(
           partial, nblocks, n_lags, reinterpret_cast<unsigned long long*>(count),
-          (stats & SKG_STAT_SUM_SQ) ? sum_sq : nullptr, (stats & SKG_STAT_SUM_SQRT) ? sum_sqrt : nullptr);
+          ((stats & SKG_STAT_SUM_SQ) || stats == 4) ? sum_sq : nullptr,
+          (stats != 4 && (stats & SKG_STAT_SUM_SQRT)) ? sum_sqrt : nullptr);
       SKG_CUDA(cudaGetLastError());
       return 0;
     }

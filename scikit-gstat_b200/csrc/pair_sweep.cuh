@@ -878,6 +878,7 @@ struct HistLaunch {
   const double* bbox8;
   unsigned long long* whist;  // STATS == 4: optional in-window |dz| histogram [n_lags][wbuckets]
   long long wbuckets;
+  const DzTable* dzt_dev;     // the |dz| window table in device memory (window kernel, STATS == 4)
 };
 
 template <int DIM, int DIR, int STATS, int EMAX, bool PRIV, bool VM>

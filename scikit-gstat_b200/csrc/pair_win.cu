@@ -109,6 +109,16 @@ __device__ __forceinline__ void flush_row(unsigned saddr, unsigned caddr, double
         "add.u32 c, c, %1;\n\t"
         "st.shared.u32 [%0], c;\n\t}"
         :: "r"(caddr), "r"(cnt));
+  } else if (STATS == 4) {  // sq carries the below-window count of the class (exact: < 2^32)
+    const unsigned below = (unsigned)__double2int_rn(sq);
+    asm volatile(
+        "{\n\t.reg .b32 b, c;\n\t"
+        "ld.shared.u32 b, [%0];\n\t"
+        "ld.shared.u32 c, [%1];\n\t"
+        "add.u32 b, b, %2;\n\tadd.u32 c, c, %3;\n\t"
+        "st.shared.u32 [%0], b;\n\t"
+        "st.shared.u32 [%1], c;\n\t}"
+        :: "r"(saddr), "r"(caddr), "r"(below), "r"(cnt));
   } else if (STATS == 3) {
     asm volatile(
         "{\n\t.reg .b64 tb, rb;\n\t.reg .f64 t, u;\n\t.reg .b32 c;\n\t"
@@ -162,9 +172,15 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
                      const unsigned int* __restrict__ tile_list,
                      const unsigned long long* __restrict__ counters,
                      const double* __restrict__ bbox32, const double* __restrict__ bbox8,
-                     double wlo, double whi, int js) {
+                     double wlo, double whi, int js, const DzTable* __restrict__ dzt,
+                     unsigned long long* __restrict__ whist, long long wbuckets) {
+  // STATS == 4 (Dowd's windowed median, skg_pair_dz_windows): per class the pair count, the count of
+  // |dz| below the class's window [lo, hi) and - rare - an atomic into the window's bucket histogram
   __shared__ double2 sXY[TILE + 2];
   __shared__ double sZ[TILE + 2];
+  __shared__ double sDzLo[STATS == 4 ? THR_MAX + 2 : 1];
+  __shared__ double sDzHi[STATS == 4 ? THR_MAX + 2 : 1];
+  __shared__ double sDzSc[STATS == 4 ? THR_MAX + 2 : 1];
   __shared__ double sThrD[THR_MAX + 2];  // thresholds as doubles, +inf beyond the last class
   __shared__ uint16_t sLut[LUT_MAX];     // lut[cell] * 8
   __shared__ double sGB[TILE / 8][4];    // boxes of the current chunk's j groups
@@ -181,6 +197,13 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
   for (int k = tid; k < THR_MAX + 2; k += WB)
     sThrD[k] = k < nb ? __longlong_as_double((long long)tab.thr[k]) : inf;
   for (int k = tid; k < tab.ncell; k += WB) sLut[k] = (uint16_t)(tab.lut[k] * 8);
+  if (STATS == 4) {
+    for (int k = tid; k < THR_MAX + 2; k += WB) {  // classes beyond the last edge: empty windows
+      sDzLo[k] = k < nb ? dzt->lo[k] : 0.0;
+      sDzHi[k] = k < nb ? dzt->hi[k] : 0.0;
+      sDzSc[k] = k < nb ? dzt->scale[k] : 0.0;
+    }
+  }
   {
     unsigned long long* z = reinterpret_cast<unsigned long long*>(acc_raw);
     for (int k = tid; k < NR * (WB * (SUMB + 4) / 8); k += WB) z[k] = 0ull;
@@ -286,12 +309,33 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
           if (DIAG) gg = (jbeg + jj <= r * WB + tid) ? nbS : gg;  // keep i < j only
           g[r] = gg;
           dz[r] = zi[r] - zj;
+          if (STATS == 4) {
+            // flag for rmw_split<4> (+1: below the window) with the bucket of an in-window key
+            // folded in as -(slot + 1): the atomic itself waits for accumulate(), because the
+            // pipeline's look-ahead entry is evaluated here but never accumulated
+            const double ad = fabs(dz[r]);
+            const unsigned lg = min(gg, nbS) / GS;
+            const double lo = sDzLo[lg];
+            double flag = (ad < lo) ? 1.0 : 0.0;
+            if (whist && gg < nbS && ad >= lo && ad < sDzHi[lg]) {
+              long long bk = __double2ll_rz(__dmul_rn(__dsub_rn(ad, lo), sDzSc[lg]));
+              bk = bk < wbuckets - 1 ? bk : wbuckets - 1;
+              flag = -(double)((long long)lg * wbuckets + bk + 1);
+            }
+            dz[r] = flag;
+          }
         }
       };
       auto accumulate = [&](const unsigned (&g)[WR], const double (&dz)[WR]) {
 #pragma unroll
-        for (int r = 0; r < WR; ++r)
-          rmw_split<STATS>(aSum + g[r] * SROW, aCnt + g[r] * CROW, dz[r], g[r] < nbS ? 1 : 0);
+        for (int r = 0; r < WR; ++r) {
+          double v = dz[r];
+          if (STATS == 4 && v < 0.0) {  // in-window key: its bucket (exact in a double: < 2^32 slots)
+            atomicAdd(&whist[(long long)(-v) - 1], 1ull);
+            v = 0.0;
+          }
+          rmw_split<STATS>(aSum + g[r] * SROW, aCnt + g[r] * CROW, v, g[r] < nbS ? 1 : 0);
+        }
       };
       unsigned gA[WR], gB[WR];
       double dA[WR], dB[WR];
@@ -347,6 +391,59 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
         continue;
       }
       SKG_DBG(all2 ? 1 : 2);
+      if (STATS == 4) {
+        // |dz| windows of the (up to three) classes of each point's lag window, in registers
+        double wl[WR][3], wh[WR][3];
+        unsigned cb[WR][3], c1[WR], c2[WR];
+#pragma unroll
+        for (int r = 0; r < WR; ++r) {
+          const unsigned b = gb[r] / GS;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { wl[r][k] = sDzLo[b + k]; wh[r][k] = sDzHi[b + k]; cb[r][k] = 0u; }
+          c1[r] = c2[r] = 0u;
+        }
+#pragma unroll 2
+        for (int jj = g0; jj < g0 + G; ++jj) {
+          const double2 pj = sXY[jj];
+          const double zj = sZ[jj];
+#pragma unroll
+          for (int r = 0; r < WR; ++r) {
+            bool p1 = false, p2 = false;
+            if (!all1) {  // one class for the whole group: no distance needed
+              const double dx = xi[r] - pj.x;
+              const double dy = yi[r] - pj.y;
+              const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              p1 = s >= T1[r];
+              p2 = !all2 && s >= T2[r];
+            }
+            const double ad = fabs(zi[r] - zj);
+            const double lo = p2 ? wl[r][2] : (p1 ? wl[r][1] : wl[r][0]);
+            const double hi = p2 ? wh[r][2] : (p1 ? wh[r][1] : wh[r][0]);
+            const bool below = ad < lo;
+            c1[r] += p1 ? 1u : 0u;
+            c2[r] += p2 ? 1u : 0u;
+            cb[r][0] += (below && !p1) ? 1u : 0u;
+            cb[r][1] += (below && p1 && !p2) ? 1u : 0u;
+            cb[r][2] += (below && p2) ? 1u : 0u;
+            if (whist && !below && ad < hi) {  // ~8 % of the in-range pairs
+              const unsigned lg = gb[r] / GS + (p2 ? 2u : (p1 ? 1u : 0u));
+              long long bk = __double2ll_rz(__dmul_rn(__dsub_rn(ad, lo), sDzSc[lg]));
+              bk = bk < wbuckets - 1 ? bk : wbuckets - 1;
+              atomicAdd(&whist[(long long)lg * wbuckets + bk], 1ull);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < WR; ++r) {
+          const unsigned g8 = gb[r];
+          flush_row<4>(aSum + g8 * SROW, aCnt + g8 * CROW, (double)cb[r][0], 0.0, (unsigned)G - c1[r]);
+          if (!all1)
+            flush_row<4>(aSum + (g8 + 8) * SROW, aCnt + (g8 + 8) * CROW, (double)cb[r][1], 0.0, c1[r] - c2[r]);
+          if (!all2)
+            flush_row<4>(aSum + (g8 + 16) * SROW, aCnt + (g8 + 16) * CROW, (double)cb[r][2], 0.0, c2[r]);
+        }
+        continue;
+      }
       if (all1) {
         // one class for every pair of the group: no distance is evaluated at all
         double q[WR], rs[WR];
@@ -484,13 +581,14 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
       const int th = lane + 32 * k;
       const unsigned char* sp = acc_raw + (size_t)(gI * WB + th) * SUMB;
       c += *reinterpret_cast<const unsigned int*>(acc_raw + (size_t)NR * (WB * SUMB) + (size_t)(gI * WB + th) * 4);
-      if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(sp);
+      if (STATS == 4) a += (double)*reinterpret_cast<const unsigned int*>(sp);
+      else if (STATS & SKG_STAT_SUM_SQ) a += *reinterpret_cast<const double*>(sp);
       if (STATS == 2) b += *reinterpret_cast<const double*>(sp);
       if (STATS == 3) b += *reinterpret_cast<const double*>(sp + 8);
     }
     c = warp_sum(c);
-    if (STATS & SKG_STAT_SUM_SQ) a = warp_sum(a);
-    if (STATS & SKG_STAT_SUM_SQRT) b = warp_sum(b);
+    if ((STATS & SKG_STAT_SUM_SQ) || STATS == 4) a = warp_sum(a);
+    if ((STATS & SKG_STAT_SUM_SQRT) && STATS != 4) b = warp_sum(b);
     if (lane == 0) {
       out[gI].count = c;
       out[gI].sum_sq = a;
@@ -502,7 +600,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
 // ------------------------------------------------------------------ host ---
 
 size_t hist_win_smem_bytes(int nb, int stats) {
-  const int sumb = stats == 3 ? 16 : (stats == 0 ? 0 : 8);
+  const int sumb = stats == 3 ? 16 : (stats == 0 ? 0 : (stats == 4 ? 4 : 8));
   return ((size_t)(nb + 3) * WB * (sumb + 4) + 15) & ~(size_t)15;
 }
 
@@ -524,7 +622,8 @@ static int launch_hist_win_t(const HistLaunch& L) {
   if (grid > L.max_blocks) grid = L.max_blocks;
   *L.nblocks_out = (int)grid;
   kern<<<(unsigned)grid, WB, L.smem, L.st>>>(L.coords, L.values, L.n, *L.tab, L.partial, L.list,
-                                             L.list_count, L.bbox32, L.bbox8, L.wlo, L.whi, L.js);
+                                             L.list_count, L.bbox32, L.bbox8, L.wlo, L.whi, L.js, L.dzt_dev,
+                                             L.whist, L.wbuckets);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -543,6 +642,7 @@ int dispatch_hist_win(int emax, int stats, const HistLaunch& L) {
   win_plan_kernel<<<1, 256, 0, L.st>>>(L.bbox8, nt * (TILE / 8), last, L.tab->nb, force_g,
                                        const_cast<unsigned long long*>(L.list_count));
   SKG_CUDA(cudaGetLastError());
+  if (stats == 4) return emax <= 1 ? launch_hist_win_t<4, 1>(L) : launch_hist_win_t<4, 0>(L);
   if (emax <= 1) {
     if (stats == 0) return launch_hist_win_t<0, 1>(L);
     if (stats == 1) return launch_hist_win_t<1, 1>(L);
