@@ -22,8 +22,13 @@ except Exception:  # pragma: no cover
     dist = None
 
 
+LOCAL = "local"   # pseudo group: this process alone, whatever torch.distributed's state
+
+
 def world(group=None) -> Tuple[int, int]:
-    """(rank, world_size) of the process group; (0, 1) when not initialised."""
+    """(rank, world_size) of the process group; (0, 1) when not initialised or for LOCAL."""
+    if isinstance(group, str) and group == LOCAL:
+        return 0, 1
     if dist is None or not dist.is_available() or not dist.is_initialized():
         return 0, 1
     return dist.get_rank(group), dist.get_world_size(group)

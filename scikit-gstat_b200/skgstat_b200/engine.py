@@ -145,6 +145,7 @@ class PairEngine:
         # sweeps run over a Z-order sorted copy; materialising accessors need the
         # caller's order (condensed index) and use an unsorted copy made on demand
         self._orig_coords = c
+        self._sq_ub = None
         self._perm_host = None
         self._host_coords_sorted = None
         self._values_unsorted = None
@@ -153,8 +154,12 @@ class PairEngine:
             if self.n > 64:
                 ct = np.ascontiguousarray(c.T)
                 with np.errstate(invalid="ignore"):
-                    lo = np.nan_to_num(np.array([np.nanmin(r) for r in ct]))
-                    ext = np.nan_to_num(np.array([np.nanmax(r) for r in ct]) - lo)
+                    lo_raw = np.array([np.nanmin(r) for r in ct])
+                    ext_raw = np.array([np.nanmax(r) for r in ct]) - lo_raw
+                    lo = np.nan_to_num(lo_raw)
+                    ext = np.nan_to_num(ext_raw)
+                ub = float(np.sum(ext_raw * ext_raw)) * (1.0 + 1e-12)   # same value sq_upper_bound() forms
+                self._sq_ub = ub if ub > 0.0 else 1.0
                 keys = torch.empty(self.n, dtype=torch.int64, device=self.device)
                 rc = self.lib.skg_morton_keys(_ptr(self._coords_unsorted), self.n, self.dim,
                                               _hptr(lo), _hptr(ext), _ptr(keys), self._stream())
@@ -339,10 +344,12 @@ class PairEngine:
 
     def sq_upper_bound(self) -> float:
         """A value >= every squared pair distance (bounding-box diagonal, padded)."""
-        ct = np.ascontiguousarray(self._orig_coords.T)
-        ext = np.array([np.nanmax(r) - np.nanmin(r) for r in ct]) if self.n else np.zeros(self.dim)
-        ub = float(np.sum(ext * ext)) * (1.0 + 1e-12)
-        return ub if ub > 0.0 else 1.0
+        if self._sq_ub is None:
+            ct = np.ascontiguousarray(self._orig_coords.T)
+            ext = np.array([np.nanmax(r) - np.nanmin(r) for r in ct]) if self.n else np.zeros(self.dim)
+            ub = float(np.sum(ext * ext)) * (1.0 + 1e-12)
+            self._sq_ub = ub if ub > 0.0 else 1.0
+        return self._sq_ub
 
     # ------------------------------------------------- guard-band resolution
     AMB_CAPACITY = 1 << 24
@@ -770,14 +777,14 @@ class PairEngine:
     _select_mode = "auto"                  # "cells": always the log-cell sweep (tests)
 
     def _subsample_engine(self):
-        """The same fixed-seed sub-sample of the points on every rank.  Like every engine it shards
-        its sweeps over the default process group when one is initialised; all ranks walk through
-        the same calls, so they derive identical windows."""
+        """The same fixed-seed sub-sample of the points on every rank, swept by every rank on its own
+        (group LOCAL): the problem is tiny, its collectives and synchronisations would cost more than
+        its sweeps, and identical inputs give identical windows on all ranks."""
         if self._sub_engine is None:
             m = min(self.n, self.SUBSAMPLE_POINTS)
             idx = np.sort(np.random.default_rng(777).choice(self.n, size=m, replace=False))
             self._sub_idx = idx
-            self._sub_engine = PairEngine(self._orig_coords[idx], None, device=self.device)
+            self._sub_engine = PairEngine(self._orig_coords[idx], None, device=self.device, group=D.LOCAL)
         return self._sub_engine
 
     def _window_cell_counts(self, rank_fn, hi_bits: int, limit):
