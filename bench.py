@@ -61,9 +61,9 @@ NCU = {
     "matheron": {"fp64_pipe_pct": 58.7, "issue_active_pct": 61.4, "smem_wavefronts_pct": 30.7,
                  "traffic_bytes": 6692352,
                  "from": "profiles/r2_pair_hist_win_ncu_summary.txt (N=200k, 11.07 ms under ncu)"},
-    "kriging": {"fp64_pipe_pct": 6.3, "issue_active_pct": 40.5, "smem_wavefronts_pct": 49.4,
-                "traffic_bytes": 245.0e6,
-                "from": "profiles/r2_krige_chol_ncu_summary.txt (400x400 targets, 9.21 ms under ncu)"},
+    "kriging": {"fp64_pipe_pct": 7.3, "issue_active_pct": 40.6, "smem_wavefronts_pct": 40.6,
+                "traffic_bytes": 244.2e6,
+                "from": "profiles/r2_krige_chol_ncu_summary.txt (400x400 targets, 8.66 ms under ncu)"},
 }
 
 
