@@ -390,7 +390,7 @@ def run_own(args):
     step_ms, kern_ms = max_over_ranks(step_ms), max_over_ranks(kern_ms)
     e2e_steps = max(3, min(args.steps, 10))
     e2e_s, h2d, d2h, exp = e2e_leg(
-        X, lambda: skg.Variogram(c3.copy(), v3.copy(), estimator="cressie", n_lags=N_LAGS, maxlag="median",
+        X, lambda: skg.Variogram(c3, v3, estimator="cressie", n_lags=N_LAGS, maxlag="median",
                                  fit_method=None, process_group=X.group).experimental, e2e_steps)
     assert np.allclose(exp, V3.experimental, rtol=1e-12)
     out = None
@@ -419,10 +419,10 @@ def run_own(args):
     sm, km, info_m, _, _ = fused_leg(X, c3, v3, "matheron", max(3, args.steps // 2), 3, edges3)
     sm, km = max_over_ranks(sm), max_over_ranks(km)
     em_s, _, _, _ = e2e_leg(
-        X, lambda: skg.Variogram(c3.copy(), v3.copy(), estimator="matheron", n_lags=N_LAGS, maxlag="median",
+        X, lambda: skg.Variogram(c3, v3, estimator="matheron", n_lags=N_LAGS, maxlag="median",
                                  fit_method=None, process_group=X.group).experimental, 3, warm=1)
     ed_s, dh2d, dd2h, _ = e2e_leg(
-        X, lambda: skg.Variogram(c3.copy(), v3.copy(), estimator="dowd", n_lags=N_LAGS, maxlag="median",
+        X, lambda: skg.Variogram(c3, v3, estimator="dowd", n_lags=N_LAGS, maxlag="median",
                                  fit_method=None, process_group=X.group).experimental, 3, warm=1)
     if rank == 0:
         out["config3_matheron"] = {
@@ -443,7 +443,7 @@ def run_own(args):
     s2, k2, info2, l2, _ = fused_leg(X, c2, v2, "matheron", args.steps, args.warmup, V2.bins)
     s2, k2 = max_over_ranks(s2), max_over_ranks(k2)
     e2_s, h2, d2, exp2 = e2e_leg(
-        X, lambda: skg.Variogram(c2.copy(), v2.copy(), n_lags=N_LAGS, maxlag="median", fit_method=None,
+        X, lambda: skg.Variogram(c2, v2, n_lags=N_LAGS, maxlag="median", fit_method=None,
                                  process_group=X.group).experimental, max(5, args.steps), warm=5)
     assert np.allclose(exp2, V2.experimental, rtol=1e-12)
     if rank == 0:
@@ -459,7 +459,7 @@ def run_own(args):
     # ---------------------------------------------------------------- config 4 (directional, uniform)
     c4, v4 = make_inputs(**C4)
     pairs4 = C4["n"] * (C4["n"] - 1) // 2
-    mk4 = lambda: skg.DirectionalVariogram(c4.copy(), v4.copy(), azimuth=45, tolerance=22.5, bin_func="uniform",
+    mk4 = lambda: skg.DirectionalVariogram(c4, v4, azimuth=45, tolerance=22.5, bin_func="uniform",
                                            n_lags=10, fit_method=None, process_group=X.group)
     D4 = mk4()
     _ = D4.experimental

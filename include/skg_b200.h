@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SKG_ABI_VERSION 5
+#define SKG_ABI_VERSION 6
 #define SKG_TILE 256            /* points per tile edge                          */
 #define SKG_MAX_LAGS 250        /* upper bound for n_lags                        */
 #define SKG_KRIGE_MAX_POINTS 128 /* max_points supported by the warp-per-target kernels (<= 64: the fast layout) */
@@ -271,6 +271,29 @@ int skg_pair_select_gather(const double* coords, const double* values, int n_val
                            double* cand_key, uint32_t* cand_slot, uint64_t* cand_count,
                            int64_t capacity, void* scratch, int64_t scratch_bytes,
                            int64_t tile_begin, int64_t tile_end, int64_t tile_stride, void* stream);
+
+/* Order statistics of the gathered candidates, picked where they lie (no sort, no host round
+ * trip for the candidate count): for each wanted slot want_slot[k] the keys among the first
+ * min(*cand_count, capacity) candidates carrying that slot are ranked, and
+ *   out[k]                      = number of candidates with that slot          (k < n_want)
+ *   out[n_want + r]             = the key of rank want_rank[r] inside its slot
+ *                                 (want_off[k] <= r < want_off[k+1]; 0 if the rank is absent)
+ * The two values np.median / np.percentile interpolate between (Variogram.py:1288-1293,
+ * binning.py:70-79, estimators.py:178) come back in one small copy.  want_* are HOST arrays
+ * (n_want <= 32, at most 64 ranks in total); keys/slots/count/out/scratch are device pointers.
+ * capacity <= SKG_PICK_DIRECT_MAX: one launch, ranks by counting (O(m^2) compares), the key
+ * windows and scratch may be NULL.  Larger: want_lo_bits/want_hi_bits[k] bound the bit patterns
+ * of the slot's (non-negative) keys; a histogram linear in the key bits narrows each rank to a
+ * bucket whose keys are then ranked by counting (4 launches, scratch >= skg_pick_scratch_bytes()).
+ * If more than 4096 keys share a wanted bucket (heavy ties) out[k] = -1 for that slot and the
+ * caller has to sort. */
+#define SKG_PICK_DIRECT_MAX 16384
+int64_t skg_pick_scratch_bytes(void);
+int skg_pick_order_stats(const double* cand_key, const uint32_t* cand_slot, const uint64_t* cand_count,
+                         int64_t capacity, const uint32_t* want_slot, const int32_t* want_off,
+                         const int64_t* want_rank, const uint64_t* want_lo_bits,
+                         const uint64_t* want_hi_bits, int n_want, double* out, void* scratch,
+                         int64_t scratch_bytes, void* stream);
 
 /* Materialising accessors (Variogram.distance :1202, pairwise_diffs :592-606,
  * lag_groups :1514-1533, DirectionalVariogram._direction_mask :605-624) for the

@@ -170,6 +170,175 @@ static int launch_cellcount(const double* coords, int64_t n, const DirParams& dp
   return 0;
 }
 
+// Order statistics of gathered candidates without a sort: candidate i of a wanted slot finds its
+// rank by counting the candidates of the same slot below it (ties broken by position), and the
+// one whose rank is wanted writes its key.  O(m^2) compares over the whole grid: for the few
+// thousand keys a narrowed select window leaves this is a few microseconds and replaces a dozen
+// library launches (two sorts, two searches, index arithmetic) of the host-driven pick.
+constexpr int PICK_THREADS = 256;
+constexpr int PICK_MAX_WANT = 32;
+constexpr int PICK_MAX_RANKS = 64;
+struct PickPlan {
+  int n_want;
+  int slot[PICK_MAX_WANT];
+  int off[PICK_MAX_WANT + 1];
+  long long rank[PICK_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(PICK_THREADS)
+pick_ranks_kernel(const double* __restrict__ keys, const int* __restrict__ slots,
+                  const unsigned long long* __restrict__ count, long long cap, PickPlan plan,
+                  double* __restrict__ out) {
+  __shared__ double sK[PICK_THREADS];
+  __shared__ int sS[PICK_THREADS];
+  long long m = (long long)*count;
+  if (m > cap) m = cap;
+  const long long i = (long long)blockIdx.x * PICK_THREADS + threadIdx.x;
+  if ((long long)blockIdx.x * PICK_THREADS >= m) return;
+  const bool live = i < m;
+  const int my_slot = live ? slots[i] : 0;
+  const double my_key = live ? keys[i] : 0.0;
+  int w = -1;
+  if (live)
+    for (int k = 0; k < plan.n_want; ++k)
+      if (plan.slot[k] == my_slot) w = k;
+  long long below = 0, total = 0;
+  for (long long base = 0; base < m; base += PICK_THREADS) {
+    const long long j = base + threadIdx.x;
+    sK[threadIdx.x] = j < m ? keys[j] : 0.0;
+    sS[threadIdx.x] = j < m ? slots[j] : 0;
+    __syncthreads();
+    if (w >= 0) {
+      const int lim = (int)(m - base < PICK_THREADS ? m - base : PICK_THREADS);
+      for (int t = 0; t < lim; ++t) {
+        const bool same = sS[t] == my_slot;
+        const double k = sK[t];
+        total += same;
+        below += same && (k < my_key || (k == my_key && base + t < i));
+      }
+    }
+    __syncthreads();
+  }
+  if (w < 0) return;
+  if (below == 0) out[w] = (double)total;   // exactly one candidate per slot has rank 0
+  for (int r = plan.off[w]; r < plan.off[w + 1]; ++r)
+    if (plan.rank[r] == below) out[plan.n_want + r] = my_key;
+}
+
+// More candidates than ranking by counting can take: one linear-in-bits histogram per wanted
+// slot narrows every wanted rank to one of PICK_BUCKETS buckets, the keys of those buckets are
+// appended to short lists, and the rank is found by counting inside its list.  Four launches, all
+// decisions on the device; a bucket that overflows its list (heavy ties) reports -1 as the slot
+// count and the caller sorts instead.
+constexpr int PICK_BUCKETS = 2048;
+constexpr int PICK_LIST = 4096;
+struct PickWide {
+  unsigned long long lo[PICK_MAX_WANT];
+  int shift[PICK_MAX_WANT];
+};
+
+__device__ __forceinline__ int pick_bucket(double key, unsigned long long lo, int shift) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(key);
+  if (b <= lo) return 0;
+  const unsigned long long q = (b - lo) >> shift;
+  return q < (unsigned long long)PICK_BUCKETS ? (int)q : PICK_BUCKETS - 1;
+}
+
+__global__ void __launch_bounds__(PICK_THREADS)
+pick_hist_kernel(const double* __restrict__ keys, const int* __restrict__ slots,
+                 const unsigned long long* __restrict__ count, long long cap, PickPlan plan, PickWide wide,
+                 unsigned int* __restrict__ hist) {
+  long long m = (long long)*count;
+  if (m > cap) m = cap;
+  for (long long i = (long long)blockIdx.x * PICK_THREADS + threadIdx.x; i < m;
+       i += (long long)gridDim.x * PICK_THREADS) {
+    const int sl = slots[i];
+    for (int k = 0; k < plan.n_want; ++k)
+      if (plan.slot[k] == sl) atomicAdd(&hist[k * PICK_BUCKETS + pick_bucket(keys[i], wide.lo[k], wide.shift[k])], 1u);
+  }
+}
+
+// one CTA per wanted rank r: bucket holding it and the number of keys below that bucket
+__global__ void __launch_bounds__(PICK_THREADS)
+pick_locate_kernel(PickPlan plan, const unsigned int* __restrict__ hist, int* __restrict__ q_bucket,
+                   long long* __restrict__ q_below, double* __restrict__ out) {
+  __shared__ long long sPart[PICK_THREADS];
+  const int r = blockIdx.x;
+  int w = 0;
+  while (w + 1 < plan.n_want && plan.off[w + 1] <= r) ++w;
+  const unsigned int* h = hist + (size_t)w * PICK_BUCKETS;
+  constexpr int PER = PICK_BUCKETS / PICK_THREADS;
+  long long mine = 0;
+  for (int t = 0; t < PER; ++t) mine += h[threadIdx.x * PER + t];
+  sPart[threadIdx.x] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < PICK_THREADS; ++t) { const long long v = sPart[t]; sPart[t] = run; run += v; }
+    if (r == plan.off[w]) out[w] = (double)run;
+    q_bucket[r] = -1;
+    q_below[r] = 0;
+  }
+  __syncthreads();
+  long long below = sPart[threadIdx.x];
+  const long long want = plan.rank[r];
+  for (int t = 0; t < PER; ++t) {
+    const long long c = h[threadIdx.x * PER + t];
+    if (want >= below && want < below + c) { q_bucket[r] = threadIdx.x * PER + t; q_below[r] = below; }
+    below += c;
+  }
+}
+
+__global__ void __launch_bounds__(PICK_THREADS)
+pick_collect_kernel(const double* __restrict__ keys, const int* __restrict__ slots,
+                    const unsigned long long* __restrict__ count, long long cap, PickPlan plan, PickWide wide,
+                    const int* __restrict__ q_bucket, double* __restrict__ lists, unsigned int* __restrict__ q_len) {
+  long long m = (long long)*count;
+  if (m > cap) m = cap;
+  for (long long i = (long long)blockIdx.x * PICK_THREADS + threadIdx.x; i < m;
+       i += (long long)gridDim.x * PICK_THREADS) {
+    const int sl = slots[i];
+    for (int k = 0; k < plan.n_want; ++k) {
+      if (plan.slot[k] != sl) continue;
+      const double key = keys[i];
+      const int b = pick_bucket(key, wide.lo[k], wide.shift[k]);
+      for (int r = plan.off[k]; r < plan.off[k + 1]; ++r) {
+        if (q_bucket[r] != b) continue;
+        const unsigned int p = atomicAdd(&q_len[r], 1u);
+        if (p < (unsigned)PICK_LIST) lists[(size_t)r * PICK_LIST + p] = key;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PICK_THREADS)
+pick_list_kernel(PickPlan plan, const double* __restrict__ lists, const unsigned int* __restrict__ q_len,
+                 const long long* __restrict__ q_below, const int* __restrict__ q_bucket,
+                 double* __restrict__ out) {
+  __shared__ double sK[PICK_LIST];
+  const int r = blockIdx.x;
+  int w = 0;
+  while (w + 1 < plan.n_want && plan.off[w + 1] <= r) ++w;
+  if (q_bucket[r] < 0) return;                      // rank beyond the slot's keys: value stays 0
+  const unsigned int len = q_len[r];
+  if (len > (unsigned)PICK_LIST) {                  // too many keys share the bucket: caller sorts
+    if (threadIdx.x == 0) out[w] = -1.0;
+    return;
+  }
+  for (unsigned int t = threadIdx.x; t < len; t += PICK_THREADS) sK[t] = lists[(size_t)r * PICK_LIST + t];
+  __syncthreads();
+  const long long want = plan.rank[r] - q_below[r];
+  for (unsigned int i = threadIdx.x; i < len; i += PICK_THREADS) {
+    const double mine = sK[i];
+    long long below = 0;
+    for (unsigned int t = 0; t < len; ++t) {
+      const double k = sK[t];
+      below += (k < mine) || (k == mine && t < i);
+    }
+    if (below == want) out[plan.n_want + r] = mine;
+  }
+}
+
 }  // namespace skg
 
 using namespace skg;
@@ -221,6 +390,91 @@ int skg_pair_cell_counts(const double* coords, int64_t n, int dim, const double*
   else if (use_dir == 2) rc = launch_cellcount<2, 2>(coords, n, dp, lo_bits, hi_bits, shift, key0, cnt, ntl, js, S, win.lo[0], win.hi[0], st);
   else rc = launch_cellcount<2, 0>(coords, n, dp, lo_bits, hi_bits, shift, key0, cnt, ntl, js, S, win.lo[0], win.hi[0], st);
   if (rc) return rc;
+  SKG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t skg_pick_scratch_bytes(void) {
+  return (int64_t)PICK_MAX_WANT * PICK_BUCKETS * 4 + (int64_t)PICK_MAX_RANKS * (PICK_LIST * 8 + 4 + 8 + 4) + 256;
+}
+
+int skg_pick_order_stats(const double* keys, const uint32_t* slots, const uint64_t* count, int64_t capacity,
+                         const uint32_t* want_slot, const int32_t* want_off, const int64_t* want_rank,
+                         const uint64_t* want_lo_bits, const uint64_t* want_hi_bits, int n_want,
+                         double* out, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!keys || !slots || !count || !want_slot || !want_off || !want_rank || !out || capacity < 0) {
+    set_error("skg_pick_order_stats: NULL argument or negative capacity");
+    return SKG_E_BADARG;
+  }
+  if (n_want < 0 || n_want > PICK_MAX_WANT || want_off[0] != 0) {
+    set_error("skg_pick_order_stats: n_want outside [0, 32] or want_off[0] != 0");
+    return SKG_E_BADARG;
+  }
+  PickPlan plan;
+  std::memset(&plan, 0, sizeof(plan));
+  plan.n_want = n_want;
+  for (int k = 0; k < n_want; ++k) {
+    if (want_off[k + 1] < want_off[k] || want_off[k + 1] > PICK_MAX_RANKS) {
+      set_error("skg_pick_order_stats: want_off not ascending or more than 64 ranks");
+      return SKG_E_BADARG;
+    }
+    plan.slot[k] = (int)want_slot[k];
+    plan.off[k + 1] = want_off[k + 1];
+  }
+  const int n_ranks = plan.off[n_want];
+  for (int r = 0; r < n_ranks; ++r) plan.rank[r] = want_rank[r];
+  const bool wide = capacity > SKG_PICK_DIRECT_MAX;
+  if (wide && (!want_lo_bits || !want_hi_bits || !scratch || scratch_bytes < skg_pick_scratch_bytes())) {
+    set_error("skg_pick_order_stats: capacity > %d needs the key windows and skg_pick_scratch_bytes() of scratch",
+              SKG_PICK_DIRECT_MAX);
+    return SKG_E_BADARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_out = n_want + n_ranks;
+  if (n_out == 0) return 0;
+  SKG_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_out, st));
+  if (capacity == 0) return 0;
+  const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(count);
+  const int* sl = reinterpret_cast<const int*>(slots);
+  if (!wide) {
+    const int64_t grid = (capacity + PICK_THREADS - 1) / PICK_THREADS;
+    pick_ranks_kernel<<<(unsigned)grid, PICK_THREADS, 0, st>>>(keys, sl, cnt, (long long)capacity, plan, out);
+    SKG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (n_ranks == 0) {
+    set_error("skg_pick_order_stats: the wide path needs at least one wanted rank");
+    return SKG_E_BADARG;
+  }
+  PickWide W;
+  std::memset(&W, 0, sizeof(W));
+  for (int k = 0; k < n_want; ++k) {
+    const uint64_t lo = want_lo_bits[k], hi = want_hi_bits[k] > want_lo_bits[k] ? want_hi_bits[k] : want_lo_bits[k] + 1;
+    int shift = 0;
+    while (((hi - lo) >> shift) >= (uint64_t)PICK_BUCKETS) ++shift;
+    W.lo[k] = lo;
+    W.shift[k] = shift;
+  }
+  char* base = static_cast<char*>(scratch);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(base);
+  size_t off = (size_t)PICK_MAX_WANT * PICK_BUCKETS * 4;
+  long long* q_below = reinterpret_cast<long long*>(base + off);
+  off += (size_t)PICK_MAX_RANKS * 8;
+  int* q_bucket = reinterpret_cast<int*>(base + off);
+  off += (size_t)PICK_MAX_RANKS * 4;
+  unsigned int* q_len = reinterpret_cast<unsigned int*>(base + off);
+  off += (size_t)PICK_MAX_RANKS * 4;
+  off = (off + 255) & ~(size_t)255;
+  double* lists = reinterpret_cast<double*>(base + off);
+  SKG_CUDA(cudaMemsetAsync(base, 0, off, st));
+  int64_t grid = (capacity + PICK_THREADS - 1) / PICK_THREADS;
+  const int64_t max_grid = (int64_t)sm_count() * 8;
+  if (grid > max_grid) grid = max_grid;
+  pick_hist_kernel<<<(unsigned)grid, PICK_THREADS, 0, st>>>(keys, sl, cnt, (long long)capacity, plan, W, hist);
+  pick_locate_kernel<<<n_ranks, PICK_THREADS, 0, st>>>(plan, hist, q_bucket, q_below, out);
+  pick_collect_kernel<<<(unsigned)grid, PICK_THREADS, 0, st>>>(keys, sl, cnt, (long long)capacity, plan, W,
+                                                               q_bucket, lists, q_len);
+  pick_list_kernel<<<n_ranks, PICK_THREADS, 0, st>>>(plan, lists, q_len, q_below, q_bucket, out);
   SKG_CUDA(cudaGetLastError());
   return 0;
 }

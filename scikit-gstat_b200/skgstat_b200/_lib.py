@@ -12,10 +12,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SKG_B200_LIB") or os.path.join(_HERE, "libskg_b200.so")  # env: developer builds
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 TILE = 256
 MAX_LAGS = 250
 KRIGE_MAX_POINTS = 128
+PICK_DIRECT_MAX = 16384
 
 DIR_NONE, DIR_TRIANGLE, DIR_COMPASS = 0, 1, 2
 STAT_SUM_SQ, STAT_SUM_SQRT, STAT_COUNT_BELOW = 1, 2, 4
@@ -58,6 +59,8 @@ SIGNATURES = {
                                     _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "skg_pair_select_gather": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _i64,
                                       _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p]),
+    "skg_pick_scratch_bytes": (_i64, []),
+    "skg_pick_order_stats": (_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _int, _p, _p, _i64, _p]),
     "skg_pair_materialize": (_int, [_p, _p, _int, _int, _i64, _int, _p, _p, _int, _p, _p, _p, _p,
                                     _i64, _i64, _p]),
     "skg_krige_build_grid": (_int, [_p, _i64, _int, _p, _p, _p, _p, _i64, _p]),

@@ -659,6 +659,34 @@ class PairEngine:
             # stable sort by slot, segment starts from a searchsorted, one gather, one copy back
             if not want:
                 return {}
+            n_ranks = sum(len(rel) for _, rel in want)
+            if nosync and len(want) <= 32 and n_ranks <= 64:
+                # ranked on the device by our own kernels (skg_pick_order_stats): by counting for a
+                # few thousand keys, after one narrowing histogram for more; heavy ties (-1) fall
+                # through to the sort below
+                w_slot = np.array([slot for slot, _ in want], dtype=np.uint32)
+                w_off = np.zeros(len(want) + 1, dtype=np.int32)
+                w_off[1:] = np.cumsum([len(rel) for _, rel in want])
+                w_rank = np.array([r for _, rel in want for r in rel], dtype=np.int64)
+                seg = (w_slot.astype(np.int64) // int(n_buckets)).astype(np.int64)
+                w_lo = np.ascontiguousarray(lo[seg])
+                w_hi = np.ascontiguousarray(hi[seg])
+                picked = self._buffer("pick_out", 32 + 64, torch.float64)
+                pscr = self._buffer("pick_scratch", self.lib.skg_pick_scratch_bytes(), torch.uint8)
+                with torch.cuda.device(self.device):
+                    rc = self.lib.skg_pick_order_stats(
+                        _ptr(keys), _ptr(slots), _ptr(cnt), cap, _hptr(w_slot), _hptr(w_off), _hptr(w_rank),
+                        _hptr(w_lo), _hptr(w_hi), len(want), _ptr(picked), _ptr(pscr), pscr.numel(),
+                        self._stream())
+                _lib.check(rc, "skg_pick_order_stats")
+                self.launches += 1 if cap <= _lib.PICK_DIRECT_MAX else 4
+                flat = to_host(picked[:len(want) + n_ranks])
+                if not np.any(flat[:len(want)] < 0):
+                    out, pos = {}, len(want)
+                    for w, (slot, rel) in enumerate(want):
+                        out[slot] = (int(flat[w]), {r: float(flat[pos + i]) for i, r in enumerate(rel)})
+                        pos += len(rel)
+                    return out
             slots_w = torch.tensor([int(np.array([slot], dtype=np.uint32).view(np.int32)[0]) for slot, _ in want],
                                    dtype=torch.int32, device=self.device)
             if k.numel():

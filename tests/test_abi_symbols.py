@@ -70,6 +70,20 @@ def test_argument_errors_do_not_need_a_gpu():
                            3, 1, None, C.c_void_p(8), C.c_void_p(8), None, None, 0, 0, 0, 1, None)
     assert rc == -1 and b"cross 2" in lib.skg_last_error()   # "scalar needs 1 column, cross 2, ..."
     assert lib.skg_pair_batch_max_lags() >= 64
+    rc = lib.skg_pick_order_stats(None, None, None, 0, None, None, None, None, None, 1, None, None, 0, None)
+    assert rc == -1 and b"skg_pick_order_stats" in lib.skg_last_error()
+    off = np.zeros(40, dtype=np.int32)
+    rc = lib.skg_pick_order_stats(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), 4, C.c_void_p(8),
+                                  off.ctypes.data_as(C.c_void_p), C.c_void_p(8), None, None, 33, C.c_void_p(8),
+                                  None, 0, None)
+    assert rc == -1 and b"n_want" in lib.skg_last_error()
+    wslot, wrank = np.zeros(4, dtype=np.uint32), np.zeros(4, dtype=np.int64)
+    rc = lib.skg_pick_order_stats(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), 1 << 20,
+                                  wslot.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                  wrank.ctypes.data_as(C.c_void_p), None, None,
+                                  1, C.c_void_p(8), None, 0, None)
+    assert rc == -1 and b"scratch" in lib.skg_last_error()
+    assert lib.skg_pick_scratch_bytes() > 0
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -164,3 +164,57 @@ def test_round2_entry_points_through_the_raw_abi(n):
     assert_array_equal(count.cpu().numpy(), cnt_ref)
     assert_array_equal(below.cpu().numpy().astype(np.int64), below_ref)
     assert_array_equal(hist.cpu().numpy().reshape(nl, nb), hist_ref)
+
+
+@pytest.mark.parametrize("m,cap,n_slots,decimals", [
+    (1, 8, 1, 1), (257, 300, 1, 1), (5000, 5000, 3, 1), (700, 512, 2, 1), (0, 16, 1, 1),
+    (100000, 100000, 3, 9),      # wide path: narrowing histogram, then ranking inside a bucket
+    (300000, 250000, 1, 9),      # wide path, candidates beyond the capacity ignored
+    (60000, 60000, 2, None),     # wide path, all keys equal: reports -1, the caller sorts
+])
+def test_pick_order_stats_against_numpy_partition(m, cap, n_slots, decimals):
+    """skg_pick_order_stats: ranks by counting, ties by position, only the first min(count, capacity)
+    candidates are looked at; unwanted slots (and the -1 filler) are ignored."""
+    import torch
+    lib = C.CDLL(LIB)
+    P, I64, I32 = C.c_void_p, C.c_int64, C.c_int
+    lib.skg_pick_order_stats.restype = I32
+    lib.skg_pick_order_stats.argtypes = [P, P, P, I64, P, P, P, P, P, I32, P, P, I64, P]
+    lib.skg_pick_scratch_bytes.restype = I64
+    rng = np.random.default_rng(m + cap)
+    keys = np.round(10.0 + rng.random(max(cap, 1)) * 50.0, decimals) if decimals is not None \
+        else np.full(max(cap, 1), 33.0)
+    slot_ids = np.array([7, 4096, 123456], dtype=np.uint32)[:n_slots]
+    slots = rng.choice(np.concatenate((slot_ids, [99])), size=max(cap, 1)).astype(np.uint32)
+    seen = min(m, cap)
+    slots[seen:] = np.uint32(0xFFFFFFFF)
+    want_slot, want_off, want_rank, expect_cnt, expect_val = [], [0], [], [], []
+    for sid in slot_ids:
+        mine = np.sort(keys[:seen][slots[:seen] == sid])
+        ranks = sorted({0, mine.size // 2, max(mine.size - 1, 0), (mine.size - 1) // 2}) if mine.size else [0]
+        want_slot.append(sid)
+        want_rank += ranks
+        want_off.append(len(want_rank))
+        expect_cnt.append(mine.size)
+        expect_val += [mine[r] if r < mine.size else 0.0 for r in ranks]
+    ws = np.array(want_slot, dtype=np.uint32)
+    wo = np.array(want_off, dtype=np.int32)
+    wr = np.array(want_rank, dtype=np.int64)
+    lo = np.full(len(ws), np.float64(10.0).view(np.uint64), dtype=np.uint64)
+    hi = np.full(len(ws), np.float64(60.5).view(np.uint64), dtype=np.uint64)
+    k_d = torch.from_numpy(keys).cuda()
+    s_d = torch.from_numpy(slots.view(np.int32)).cuda()
+    c_d = torch.tensor([m], dtype=torch.int64, device="cuda")
+    out = torch.full((len(ws) + len(wr),), -7.0, dtype=torch.float64, device="cuda")
+    scr = torch.empty(lib.skg_pick_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    rc = lib.skg_pick_order_stats(k_d.data_ptr(), s_d.data_ptr(), c_d.data_ptr(), cap, ws.ctypes.data,
+                                  wo.ctypes.data, wr.ctypes.data, lo.ctypes.data, hi.ctypes.data, len(ws),
+                                  out.data_ptr(), scr.data_ptr(), scr.numel(),
+                                  torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    got = out.cpu().numpy()
+    if decimals is None:
+        assert np.all(got[:len(ws)] == -1.0)     # one bucket holds every key of the slot: list overflow
+        return
+    assert_array_equal(got[:len(ws)], np.array(expect_cnt, dtype=np.float64))
+    assert_array_equal(got[len(ws):], np.array(expect_val))
