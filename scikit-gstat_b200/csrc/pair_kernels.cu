@@ -799,6 +799,8 @@ static int select_common(bool gather, const double* coords, const double* values
       }
     }
   }
+  if (gather && L.bbox8 && dz_gather_applicable(dim, use_dir, n_lags > 0, key_kind, use_mv, host_seg, nseg))
+    return launch_dz_gather(L);   // per-lag |dz| windows: value test first (pair_dzgather.cu)
   rc = use_mv ? dispatch_select_mv(gather, dim, use_dir, L)
               : dispatch_select(gather, dim, use_dir, n_lags > 0, key_kind, L);
   return rc;

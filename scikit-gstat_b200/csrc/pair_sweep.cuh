@@ -953,5 +953,7 @@ int dispatch_hist_win(int emax, int stats, const HistLaunch& L);                
 size_t hist_win_smem_bytes(int nb, int stats);
 int dispatch_select(bool gather, int dim, int dir, bool seg, int key, const SelectLaunch& L);  // pair_select.cu
 int dispatch_select_mv(bool gather, int dim, int dir, const SelectLaunch& L);                // pair_mv.cu
+bool dz_gather_applicable(int dim, int use_dir, bool seg, int key, bool use_mv, const SegTable& sg, int nseg);  // pair_dzgather.cu
+int launch_dz_gather(const SelectLaunch& L);
 
 }  // namespace skg
