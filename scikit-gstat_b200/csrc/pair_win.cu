@@ -235,6 +235,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
 #else
 #define SKG_DBG(k) do { } while (0)
 #endif
+  const bool hist_on = STATS == 4 && whist != nullptr;
   const int64_t nwork = (int64_t)counters[0];
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const unsigned int item = tile_list[w];
@@ -401,6 +402,97 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
 #pragma unroll
           for (int k = 0; k < 3; ++k) { wl[r][k] = sDzLo[b + k]; wh[r][k] = sDzHi[b + k]; cb[r][k] = 0u; }
           c1[r] = c2[r] = 0u;
+        }
+        // The classes of the window share ONE |dz| window (lag classes past the range of the field
+        // have the same median; the host merges their windows): "below" and "inside" no longer
+        // depend on the class, only their attribution does - packed cumulative counters
+        // (pairs | below << 16, at most G = 32 each) under the class predicates, no selects.
+        bool same = true;
+#pragma unroll
+        for (int r = 0; r < WR; ++r) {
+          const bool s01 = wl[r][0] == wl[r][1] && wh[r][0] == wh[r][1];
+          const bool s12 = wl[r][1] == wl[r][2] && wh[r][1] == wh[r][2];
+          same &= all1 || (s01 && (all2 || s12));
+        }
+        if (__all_sync(0xffffffffu, same)) {
+          unsigned a0[WR], a1[WR], a2[WR];
+          double lo[WR], hi[WR], sc[WR], T2x[WR];
+          unsigned long long* hrow[WR];
+#pragma unroll
+          for (int r = 0; r < WR; ++r) {
+            a0[r] = a1[r] = a2[r] = 0u;
+            lo[r] = wl[r][0];
+            hi[r] = hist_on ? wh[r][0] : lo[r];   // no histogram wanted: nothing is "inside"
+            sc[r] = sDzSc[gb[r] / GS];
+            T2x[r] = all2 ? inf : T2[r];          // two classes only: the third never fires
+            hrow[r] = whist + (long long)(gb[r] / GS) * wbuckets;
+          }
+          const int wb1 = (int)(wbuckets - 1);
+          auto inside = [&](int r, double ad, unsigned k) {   // ~7 % of the pairs
+            int bk = __double2int_rz(__dmul_rn(__dsub_rn(ad, lo[r]), sc[r]));   // saturates, then clamped
+            bk = bk < wb1 ? bk : wb1;
+            atomicAdd(hrow[r] + ((long long)k * wbuckets + bk), 1ull);
+          };
+          if (all1) {
+#pragma unroll 4
+            for (int jj = g0; jj < g0 + G; ++jj) {
+              const double zj = sZ[jj];
+#pragma unroll
+              for (int r = 0; r < WR; ++r) {
+                const double ad = fabs(zi[r] - zj);
+                unsigned inw;
+                asm("{\n\t.reg .pred x, w;\n\t.reg .u32 v;\n\t"
+                    "setp.lt.f64 x, %2, %3;\n\t"
+                    "selp.u32 v, 0x10001, 1, x;\n\t"
+                    "add.u32 %0, %0, v;\n\t"
+                    "setp.lt.and.f64 w, %2, %4, !x;\n\t"
+                    "selp.u32 %1, 1, 0, w;\n\t}"
+                    : "+r"(a0[r]), "=r"(inw) : "d"(ad), "d"(lo[r]), "d"(hi[r]));
+                if (inw) inside(r, ad, 0u);
+              }
+            }
+          } else {
+#pragma unroll 2
+            for (int jj = g0; jj < g0 + G; ++jj) {
+              const double2 pj = sXY[jj];
+              const double zj = sZ[jj];
+#pragma unroll
+              for (int r = 0; r < WR; ++r) {
+                const double dx = xi[r] - pj.x;
+                const double dy = yi[r] - pj.y;
+                const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                const double ad = fabs(zi[r] - zj);
+                unsigned inw, k;
+                asm("{\n\t.reg .pred x, p, q, w;\n\t.reg .u32 v, kq;\n\t"
+                    "setp.lt.f64 x, %5, %6;\n\t"
+                    "selp.u32 v, 0x10001, 1, x;\n\t"
+                    "add.u32 %0, %0, v;\n\t"
+                    "setp.ge.f64 p, %8, %9;\n\t"
+                    "setp.ge.f64 q, %8, %10;\n\t"
+                    "@p add.u32 %1, %1, v;\n\t"
+                    "@q add.u32 %2, %2, v;\n\t"
+                    "setp.lt.and.f64 w, %5, %7, !x;\n\t"
+                    "selp.u32 %3, 1, 0, w;\n\t"
+                    "selp.u32 %4, 1, 0, p;\n\t"
+                    "selp.u32 kq, 1, 0, q;\n\t"
+                    "add.u32 %4, %4, kq;\n\t}"
+                    : "+r"(a0[r]), "+r"(a1[r]), "+r"(a2[r]), "=r"(inw), "=r"(k)
+                    : "d"(ad), "d"(lo[r]), "d"(hi[r]), "d"(s), "d"(T1[r]), "d"(T2x[r]));
+                if (inw) inside(r, ad, k);
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < WR; ++r) {
+            const unsigned g8 = gb[r];
+            const unsigned t0 = a0[r] - a1[r], t1 = a1[r] - a2[r], t2 = a2[r];  // field-wise: no borrow
+            flush_row<4>(aSum + g8 * SROW, aCnt + g8 * CROW, (double)(t0 >> 16), 0.0, t0 & 0xffffu);
+            if (!all1)
+              flush_row<4>(aSum + (g8 + 8) * SROW, aCnt + (g8 + 8) * CROW, (double)(t1 >> 16), 0.0, t1 & 0xffffu);
+            if (!all2)
+              flush_row<4>(aSum + (g8 + 16) * SROW, aCnt + (g8 + 16) * CROW, (double)(t2 >> 16), 0.0, t2 & 0xffffu);
+          }
+          continue;
         }
 #pragma unroll 2
         for (int jj = g0; jj < g0 + G; ++jj) {

@@ -1068,7 +1068,7 @@ class PairEngine:
         return from_bits(bits) if bits > 0 else (0.0 if (self.n_pairs > 0 and dirp is None) else None)
 
     WINDOWED_MEDIAN_MIN_PAIRS = 2 * 10 ** 8   # below this the plain two-sweep select is fast enough
-    WINDOW_HALF_QUANTILE = 0.04
+    WINDOW_HALF_QUANTILE = 0.025   # ~7 sigma of the sub-sample's rank error; a miss falls back to the full range
 
     def _dz_select(self, thr, dirp, lo_bits, hi_bits, rank_fn, n_keys=None, first_hist=None, nb=None):
         """first_hist: the histogram of the first pass if a merged sweep already produced it (same
@@ -1259,7 +1259,7 @@ class PairEngine:
         if finite_values and self.n_pairs >= self.WINDOWED_MEDIAN_MIN_PAIRS and nl * 16 * 64 <= 180 * 1024:
             win = self._median_windows(thr, dirp, hi)
             if win is not None:
-                w_lo, w_hi = win                      # per-lag bit windows [lo, hi)
+                w_lo, w_hi = self._merge_dz_windows(*win, hi)   # per-lag bit windows [lo, hi)
                 if fsrc is None:
                     # one sweep: counts, below-window counts and the in-window histogram
                     nbk = 1 << 12
@@ -1312,6 +1312,37 @@ class PairEngine:
                 # np.median: mean of the two middle elements (numpy _median -> mean)
                 med[g] = a if (t % 2) else (a + b) / 2.0
         return self._unmap(np.asarray(totals, dtype=np.int64), fsrc), self._unmap(med, fsrc, fill=np.nan)
+
+    WINDOW_MERGE_GROWTH = 2.0
+
+    @classmethod
+    def _merge_dz_windows(cls, w_lo, w_hi, hi_bits_full):
+        """Runs of consecutive lag classes whose windows nearly coincide (the classes past the
+        range of the field share one median) get ONE common window, their union, as long as it
+        is at most WINDOW_MERGE_GROWTH times as wide as the widest member: the sweep then needs
+        no per-class window selection for pairs whose candidate classes lie in one run
+        (pair_win.cu, STATS == 4).  Any window that holds the median is a valid window."""
+        nl = int(w_lo.size)
+        lo = w_lo.copy()
+        hi = w_hi.copy()
+        lo_f, hi_f = w_lo.view(np.float64), w_hi.view(np.float64)
+        g = 0
+        while g < nl:
+            h = g + 1
+            if not (w_lo[g] == 0 and w_hi[g] >= hi_bits_full):      # full-range windows stay alone
+                a, b = int(w_lo[g]), int(w_hi[g])
+                width = hi_f[g] - lo_f[g]
+                while h < nl and not (w_lo[h] == 0 and w_hi[h] >= hi_bits_full):
+                    na, nb = min(a, int(w_lo[h])), max(b, int(w_hi[h]))
+                    wmax = max(width, hi_f[h] - lo_f[h])
+                    if from_bits(nb) - from_bits(na) > cls.WINDOW_MERGE_GROWTH * wmax:
+                        break
+                    a, b, width = na, nb, wmax
+                    h += 1
+                lo[g:h] = a
+                hi[g:h] = b
+            g = h
+        return lo, hi
 
     def _median_windows(self, thr, dirp, hi_bits_full):
         """Per-lag |dz| windows (bit patterns) that very probably hold the lag's median: the
