@@ -145,6 +145,7 @@ __device__ __forceinline__ void chunk_box(const double* __restrict__ bbox32, int
 
 constexpr int HB_THREADS = 64;  // threads per CTA of the fused / select sweeps (= HB)
 constexpr int SEL_GROUP = 16;   // j points per group of the select passes' group-level culling
+constexpr int SEL_MAXWIN = 32;  // distance windows the group-level test scans directly
 
 struct DzTable {  // per-lag |dz| windows of the below-count mode (STATS == 4)
   double lo[THR_MAX];     // pairs with |dz| < lo are counted "below"
@@ -612,6 +613,10 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
   __shared__ uint8_t sLut[LUT_MAX];
   __shared__ SegTable sSeg;
   __shared__ double sGB[DIM == 2 ? TILE / SEL_GROUP : 1][4];  // boxes of the chunk's 16-point j groups
+  // distance keys with lag classes: the (few) windows as high words of their bounds, for the
+  // group-level test (integer compares on truncated bounds: a superset, never a miss)
+  __shared__ uint32_t sWinLo[SEL_MAXWIN], sWinHi[SEL_MAXWIN];
+  __shared__ int sNWin;
   extern __shared__ __align__(16) unsigned char mv_raw[];  // VM: value columns of both tiles
   double* mvI = reinterpret_cast<double*>(mv_raw);
   double* mvJ = mvI + (VM ? mv.nv * TILE : 0);
@@ -625,7 +630,24 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
     sSeg.hi_bits[k] = seg_tab.hi_bits[k];
     sSeg.scale[k] = seg_tab.scale[k];
   }
+  if (tid == 0) {
+    int nw = 0;
+    if (SEG && KEY == SKG_KEY_SQDIST) {
+      for (int k = 0; k < nb; ++k) {
+        const uint64_t wl = seg_tab.lo_bits[k], wh = seg_tab.hi_bits[k];
+        if (wh <= wl) continue;
+        if (nw == SEL_MAXWIN) { nw = -1; break; }   // too many windows: class look-ups instead
+        sWinLo[nw] = (uint32_t)(wl >> 32);
+        sWinHi[nw] = (uint32_t)((wh - 1) >> 32);
+        ++nw;
+      }
+    } else {
+      nw = -1;
+    }
+    sNWin = nw;
+  }
   __syncthreads();
+  const int nwin = sNWin;
   const int shift = tab.shift, klo = tab.key0, khi = tab.key0 + tab.ncell - 1, emax = tab.emax;
   const uint8_t* lutb = sLut - klo;
   const int64_t nt = (n + TILE - 1) / TILE;
@@ -738,6 +760,11 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
         if (!SEG) {
           if (KEY == SKG_KEY_SQDIST) need |= (bmin < sSeg.hi_bits[0]) & (bmax >= sSeg.lo_bits[0]);
           else need |= sSeg.hi_bits[0] > sSeg.lo_bits[0];
+        } else if (KEY == SKG_KEY_SQDIST && nwin >= 0) {
+          const uint32_t a = (uint32_t)(bmin >> 32), b = (uint32_t)(bmax >> 32);
+          bool hit = false;
+          for (int w = 0; w < nwin; ++w) hit |= (a <= sWinHi[w]) & (b >= sWinLo[w]);
+          need |= hit;
         } else {
           const int c0 = lag_of<EMAX>(bmin, sThr, lutb, shift, klo, khi, emax);
           int c1 = lag_of<EMAX>(bmax, sThr, lutb, shift, klo, khi, emax);
@@ -775,7 +802,15 @@ pair_select_kernel(const double* __restrict__ coords, const double* __restrict__
           else gg = sb <= INF_BITS ? 0 : nb;  // NaN: padded point or NaN coordinate
           if (DIAG) gg = (jbeg + jj <= r * HB + tid) ? nb : gg;  // keep i < j only
           if (DIR) {
-            if (gg < nb && !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nb;
+            // the mask costs more than the rest of the pair: evaluate it only where the pair can
+            // still count (its segment has a window and, for distance keys, s lies inside it);
+            // the running maximum of the one-segment histogram pass looks at every masked pair
+            bool cand = gg < nb;
+            if ((SEG || GATHER) && cand) {
+              const uint64_t wl = sSeg.lo_bits[gg], wh = sSeg.hi_bits[gg];
+              cand = (KEY == SKG_KEY_SQDIST) ? (sb >= wl && sb < wh) : (wh > wl);
+            }
+            if (!cand || !dir_mask_t<DIR == 2>(dx, dy, s, dp)) gg = nb;
           }
           g[r] = gg;
           key[r] = (KEY == SKG_KEY_SQDIST) ? s
