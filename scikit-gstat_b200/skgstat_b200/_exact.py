@@ -63,12 +63,37 @@ def bucket_of(v: float, lo: float, scale: float, n_buckets: int) -> int:
 
 
 def bucket_lower_bits(b: int, lo_bits: int, hi_bits: int, scale: float, n_buckets: int) -> int:
-    """Smallest bit pattern v in [lo_bits, hi_bits] with bucket_of(v) >= b (hi_bits if none)."""
+    """Smallest bit pattern v in [lo_bits, hi_bits] with bucket_of(v) >= b (hi_bits if none).
+
+    bucket_of is monotone in v, so this is a bisection; it starts from the analytic boundary
+    lo + b / scale, brackets the true one (a few ulps away: two roundings) by doubling steps and
+    only bisects inside that bracket - a handful of evaluations instead of ~60."""
     lo_val = from_bits(lo_bits)
+
+    def reached(bits):
+        return bucket_of(from_bits(bits), lo_val, scale, n_buckets) >= b
+
     a, z = lo_bits, hi_bits
+    if z - a > 64 and scale > 0.0 and math.isfinite(scale):
+        guess = lo_val + b / scale
+        if math.isfinite(guess) and guess >= 0.0:
+            g = min(max(to_bits(guess), a), z - 1)
+            step = 1
+            if reached(g):
+                z = g
+                while z - step >= a and reached(z - step):
+                    z -= step
+                    step *= 2
+                a = max(a, z - step + 1)
+            else:
+                a = g + 1
+                while a - 1 + step < z and not reached(a - 1 + step):
+                    a += step
+                    step *= 2
+                z = min(z, a - 1 + step)
     while a < z:
         mid = (a + z) // 2
-        if bucket_of(from_bits(mid), lo_val, scale, n_buckets) >= b:
+        if reached(mid):
             z = mid
         else:
             a = mid + 1
