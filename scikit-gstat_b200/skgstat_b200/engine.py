@@ -660,7 +660,7 @@ class PairEngine:
             if not want:
                 return {}
             n_ranks = sum(len(rel) for _, rel in want)
-            if nosync and len(want) <= 32 and n_ranks <= 64:
+            if len(want) <= 32 and n_ranks <= 64:
                 # ranked on the device by our own kernels (skg_pick_order_stats): by counting for a
                 # few thousand keys, after one narrowing histogram for more; heavy ties (-1) fall
                 # through to the sort below
@@ -673,13 +673,19 @@ class PairEngine:
                 w_hi = np.ascontiguousarray(hi[seg])
                 picked = self._buffer("pick_out", 32 + 64, torch.float64)
                 pscr = self._buffer("pick_scratch", self.lib.skg_pick_scratch_bytes(), torch.uint8)
+                if nosync:
+                    pk, ps, pc, pcap = keys, slots, cnt, cap
+                else:   # the candidates of all ranks (and the guard-band pairs), count known on the host
+                    pk, ps = k.contiguous(), s.contiguous()
+                    pcap = int(pk.numel())
+                    pc = self._buffer("pick_cnt", 1, torch.int64).fill_(pcap)
                 with torch.cuda.device(self.device):
                     rc = self.lib.skg_pick_order_stats(
-                        _ptr(keys), _ptr(slots), _ptr(cnt), cap, _hptr(w_slot), _hptr(w_off), _hptr(w_rank),
+                        _ptr(pk), _ptr(ps), _ptr(pc), pcap, _hptr(w_slot), _hptr(w_off), _hptr(w_rank),
                         _hptr(w_lo), _hptr(w_hi), len(want), _ptr(picked), _ptr(pscr), pscr.numel(),
                         self._stream())
                 _lib.check(rc, "skg_pick_order_stats")
-                self.launches += 1 if cap <= _lib.PICK_DIRECT_MAX else 4
+                self.launches += 1 if pcap <= _lib.PICK_DIRECT_MAX else 4
                 flat = to_host(picked[:len(want) + n_ranks])
                 if not np.any(flat[:len(want)] < 0):
                     out, pos = {}, len(want)
