@@ -198,10 +198,14 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
     sThrD[k] = k < nb ? __longlong_as_double((long long)tab.thr[k]) : inf;
   for (int k = tid; k < tab.ncell; k += WB) sLut[k] = (uint16_t)(tab.lut[k] * 8);
   if (STATS == 4) {
-    for (int k = tid; k < THR_MAX + 2; k += WB) {  // classes beyond the last edge: empty windows
-      sDzLo[k] = k < nb ? dzt->lo[k] : 0.0;
-      sDzHi[k] = k < nb ? dzt->hi[k] : 0.0;
-      sDzSc[k] = k < nb ? dzt->scale[k] : 0.0;
+    // classes beyond the last edge repeat the last class's window, so that a group straddling the
+    // last edge still sees ONE window (shared-window loop below); their rows are never read and
+    // their in-window pairs are kept out of the histogram by the lg < nb tests
+    for (int k = tid; k < THR_MAX + 2; k += WB) {
+      const int kk = k < nb ? k : nb - 1;
+      sDzLo[k] = dzt->lo[kk];
+      sDzHi[k] = dzt->hi[kk];
+      sDzSc[k] = dzt->scale[kk];
     }
   }
   {
@@ -429,6 +433,7 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
           }
           const int wb1 = (int)(wbuckets - 1);
           auto inside = [&](int r, double ad, unsigned k) {   // ~7 % of the pairs
+            if (gb[r] / GS + k >= (unsigned)nb) return;         // beyond the last edge: not a class
             int bk = __double2int_rz(__dmul_rn(__dsub_rn(ad, lo[r]), sc[r]));   // saturates, then clamped
             bk = bk < wb1 ? bk : wb1;
             atomicAdd(hrow[r] + ((long long)k * wbuckets + bk), 1ull);
@@ -517,8 +522,8 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
             cb[r][0] += (below && !p1) ? 1u : 0u;
             cb[r][1] += (below && p1 && !p2) ? 1u : 0u;
             cb[r][2] += (below && p2) ? 1u : 0u;
-            if (whist && !below && ad < hi) {  // ~8 % of the in-range pairs
-              const unsigned lg = gb[r] / GS + (p2 ? 2u : (p1 ? 1u : 0u));
+            const unsigned lg = gb[r] / GS + (p2 ? 2u : (p1 ? 1u : 0u));
+            if (whist && !below && ad < hi && lg < (unsigned)nb) {  // ~8 % of the in-range pairs
               long long bk = __double2ll_rz(__dmul_rn(__dsub_rn(ad, lo), sDzSc[lg]));
               bk = bk < wbuckets - 1 ? bk : wbuckets - 1;
               atomicAdd(&whist[(long long)lg * wbuckets + bk], 1ull);

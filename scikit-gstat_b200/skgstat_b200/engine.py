@@ -150,9 +150,9 @@ class PairEngine:
         self._host_coords_sorted = None
         self._values_unsorted = None
         with torch.cuda.device(self.device):
-            self._coords_unsorted = to_device(c.T, self.device).view(self.dim, self.n)
+            ct = np.ascontiguousarray(c.T)          # SoA, transposed once (upload and extents)
+            self._coords_unsorted = to_device(ct, self.device).view(self.dim, self.n)
             if self.n > 64:
-                ct = np.ascontiguousarray(c.T)
                 with np.errstate(invalid="ignore"):
                     lo_raw = np.array([np.nanmin(r) for r in ct])
                     ext_raw = np.array([np.nanmax(r) for r in ct]) - lo_raw
