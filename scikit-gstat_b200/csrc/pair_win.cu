@@ -467,23 +467,21 @@ pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict
                 const double dy = yi[r] - pj.y;
                 const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                 const double ad = fabs(zi[r] - zj);
-                unsigned inw, k;
-                asm("{\n\t.reg .pred x, p, q, w;\n\t.reg .u32 v, kq;\n\t"
-                    "setp.lt.f64 x, %5, %6;\n\t"
+                unsigned inw;
+                asm("{\n\t.reg .pred x, p, q, w;\n\t.reg .u32 v;\n\t"
+                    "setp.lt.f64 x, %4, %5;\n\t"
                     "selp.u32 v, 0x10001, 1, x;\n\t"
                     "add.u32 %0, %0, v;\n\t"
-                    "setp.ge.f64 p, %8, %9;\n\t"
-                    "setp.ge.f64 q, %8, %10;\n\t"
+                    "setp.ge.f64 p, %7, %8;\n\t"
+                    "setp.ge.f64 q, %7, %9;\n\t"
                     "@p add.u32 %1, %1, v;\n\t"
                     "@q add.u32 %2, %2, v;\n\t"
-                    "setp.lt.and.f64 w, %5, %7, !x;\n\t"
-                    "selp.u32 %3, 1, 0, w;\n\t"
-                    "selp.u32 %4, 1, 0, p;\n\t"
-                    "selp.u32 kq, 1, 0, q;\n\t"
-                    "add.u32 %4, %4, kq;\n\t}"
-                    : "+r"(a0[r]), "+r"(a1[r]), "+r"(a2[r]), "=r"(inw), "=r"(k)
+                    "setp.lt.and.f64 w, %4, %6, !x;\n\t"
+                    "selp.u32 %3, 1, 0, w;\n\t}"
+                    : "+r"(a0[r]), "+r"(a1[r]), "+r"(a2[r]), "=r"(inw)
                     : "d"(ad), "d"(lo[r]), "d"(hi[r]), "d"(s), "d"(T1[r]), "d"(T2x[r]));
-                if (inw) inside(r, ad, k);
+                // the class offset is only needed inside the window: two more compares there
+                if (inw) inside(r, ad, (s >= T1[r] ? 1u : 0u) + (s >= T2x[r] ? 1u : 0u));
               }
             }
           }
