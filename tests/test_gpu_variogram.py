@@ -253,3 +253,42 @@ def test_nan_observations_follow_numpy_nan_rules(skg):
         assert_array_equal(V.bins, ref["bins"])
         assert_array_equal(V.bin_count, ref["bin_count"])
         assert_allclose(exp, ref["experimental"], rtol=1e-12, equal_nan=True)
+
+
+def test_windowed_dowd_kernels_stress(skg, monkeypatch):
+    """The large-N Dowd path (merged per-lag |dz| windows, the shared-window sweep loop, the
+    value-first gather kernel, the pick kernels) forced on at sizes the dense oracle checks:
+    ragged N, many narrow lag classes (groups spanning more than three), clustered custom edges,
+    a field without spatial structure (every class gets the same window), heavy ties and
+    constant values (degenerate windows)."""
+    from skgstat_b200.engine import PairEngine
+    monkeypatch.setattr(PairEngine, "WINDOWED_MEDIAN_MIN_PAIRS", 0)
+    monkeypatch.setattr(PairEngine, "SUBSAMPLE_POINTS", 1024)
+    rng = np.random.default_rng(5)
+    cases = []
+    c = random_points(4099, 1000.0, 2, seed=21)
+    cases.append((c, gaussian_field(c, 120.0, seed=21), dict(n_lags=25, maxlag="median")))
+    cases.append((c, gaussian_field(c, 120.0, seed=22), dict(n_lags=120, maxlag="median")))
+    cases.append((c, rng.normal(size=c.shape[0]), dict(n_lags=40, maxlag=0.6)))           # pure nugget
+    cases.append((c, gaussian_field(c, 60.0, seed=23),
+                  dict(bin_func=[5.0, 5.5, 6.0, 50.0, 50.000001, 200.0, 400.0, 401.0, 700.0], maxlag=None)))
+    c2 = random_points(3001, 500.0, 2, seed=24)
+    cases.append((c2, np.round(gaussian_field(c2, 70.0, seed=24), 1), dict(n_lags=15, maxlag="median")))  # ties
+    cases.append((c2, np.full(c2.shape[0], 3.25), dict(n_lags=10, maxlag="median")))                      # constant
+    gx, gy = np.meshgrid(np.arange(60.0), np.arange(55.0))
+    cl = np.column_stack((gx.ravel(), gy.ravel()))
+    cases.append((cl, np.round(gaussian_field(cl, 9.0, seed=3), 1), dict(n_lags=12, maxlag="median")))    # lattice
+    for coords, values, kw in cases:
+        if isinstance(kw.get("bin_func"), list):   # custom edges (Variogram.py:1119-1131): classes straight from them
+            edges = np.asarray(kw["bin_func"], dtype=float)
+            d, diffs = ov.distance(coords), ov.pairwise_diffs(values)
+            g = ov.lag_groups(d, edges)
+            cls = [diffs[np.where(g == i)] for i in range(len(edges))]
+            ref = dict(bins=edges, bin_count=np.array([x.size for x in cls]),
+                       experimental=np.array([ov.dowd(x) for x in cls]))
+        else:
+            ref = ov.dense_variogram(coords, values, "dowd", "even", kw.get("n_lags", 10), kw.get("maxlag"))
+        V = skg.Variogram(coords, values, estimator="dowd", fit_method=None, **kw)
+        assert_array_equal(V.bins, ref["bins"])
+        assert_array_equal(V.bin_count, ref["bin_count"])
+        assert_allclose(V.experimental, ref["experimental"], rtol=1e-12, atol=0.0, equal_nan=True)
