@@ -63,7 +63,7 @@ __device__ __noinline__ void dg_full_test(const DgHit& h, double xi, double yi, 
 }
 
 template <int EMAX>
-__global__ void __launch_bounds__(DG_THREADS, 4)
+__global__ void __launch_bounds__(DG_THREADS, 6)
 pair_dz_gather_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                       const __grid_constant__ BinTable tab, const __grid_constant__ SegTable seg_tab,
                       long long nbuckets, const uint32_t* __restrict__ bitmap, double* __restrict__ cand_key,
