@@ -94,6 +94,7 @@ win_plan_kernel(const double* __restrict__ bbox8, int64_t ngroups8, double last_
 constexpr int WB = SKG_WIN_THREADS;  // threads per CTA
 constexpr int WR = TILE / WB;        // "i" points per thread
 constexpr int WIN_MIN_CTAS = WB == 64 ? 6 : 4;  // register cap: 168 / 128 per thread
+constexpr int WIN_COUNT_CTAS = WB == 64 ? 8 : 6; // count-only sweeps (STATS == 0) need fewer registers: 80 per thread
 #ifndef SKG_WIN_UNROLL2
 #define SKG_WIN_UNROLL2 (SKG_WIN_THREADS == 64 ? 2 : 4)
 #endif
@@ -166,7 +167,7 @@ __device__ __forceinline__ void point_box_range(double x, double y, double lox, 
 }
 
 template <int STATS, int EMAX>
-__global__ void __launch_bounds__(WB, WIN_MIN_CTAS)
+__global__ void __launch_bounds__(WB, STATS == 0 ? WIN_COUNT_CTAS : WIN_MIN_CTAS)
 pair_hist_win_kernel(const double* __restrict__ coords, const double* __restrict__ values, int64_t n,
                      const __grid_constant__ BinTable tab, HistPartial* __restrict__ partial,
                      const unsigned int* __restrict__ tile_list,
