@@ -420,10 +420,10 @@ def run_own(args):
     sm, km = max_over_ranks(sm), max_over_ranks(km)
     em_s, _, _, _ = e2e_leg(
         X, lambda: skg.Variogram(c3, v3, estimator="matheron", n_lags=N_LAGS, maxlag="median",
-                                 fit_method=None, process_group=X.group).experimental, 3, warm=1)
+                                 fit_method=None, process_group=X.group).experimental, 5, warm=3)
     ed_s, dh2d, dd2h, _ = e2e_leg(
         X, lambda: skg.Variogram(c3, v3, estimator="dowd", n_lags=N_LAGS, maxlag="median",
-                                 fit_method=None, process_group=X.group).experimental, 3, warm=1)
+                                 fit_method=None, process_group=X.group).experimental, 5, warm=3)
     if rank == 0:
         out["config3_matheron"] = {
             "value": pairs3 / (sm * 1e-3), "unit": UNIT, "ms_per_step": sm,
@@ -463,7 +463,7 @@ def run_own(args):
                                            n_lags=10, fit_method=None, process_group=X.group)
     D4 = mk4()
     _ = D4.experimental
-    e4_s, h4, d4, _ = e2e_leg(X, lambda: mk4().experimental, 3, warm=1)
+    e4_s, h4, d4, _ = e2e_leg(X, lambda: mk4().experimental, 5, warm=3)
     s4, k4, info4, _, _ = fused_leg(X, c4, v4, "matheron", max(3, args.steps // 2), 3, D4.bins, D4._dirp())
     s4, k4 = max_over_ranks(s4), max_over_ranks(k4)
     if rank == 0:
