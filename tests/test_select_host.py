@@ -133,3 +133,62 @@ def test_single_bucket_with_known_counts_needs_no_histogram_pass():
     calls.clear()
     with pytest.raises(AssertionError):
         exact_select(1, [lo_b], [hi_b], 1, lambda g, t: ranks, rh, rg, bucket_limit=100)
+
+
+def _bisect_bucket_lower_bits(b, lo_bits, hi_bits, scale, n_buckets):
+    """Plain bisection over the bit patterns: the definition bucket_lower_bits has to meet."""
+    from skgstat_b200._exact import bucket_of
+    lo_val = from_bits(lo_bits)
+    a, z = lo_bits, hi_bits
+    while a < z:
+        mid = (a + z) // 2
+        if bucket_of(from_bits(mid), lo_val, scale, n_buckets) >= b:
+            z = mid
+        else:
+            a = mid + 1
+    return a
+
+
+def test_bucket_lower_bits_equals_plain_bisection():
+    """The bracketed search (analytic start, doubling steps) returns exactly what the ~62-step
+    bisection returns: tiny and wide windows, windows starting at 0, every bucket count used."""
+    from skgstat_b200._exact import bucket_lower_bits
+    from skgstat_b200.select import _scale_for
+    rng = np.random.default_rng(11)
+    checked = 0
+    for _ in range(600):
+        lo = float(rng.choice([0.0, rng.random() * 10, rng.random() * 1e-3, rng.random() * 1e5]))
+        width = float(rng.choice([1e-12, 1e-6, 1e-3, 1.0, 100.0])) * (rng.random() + 0.01) * max(lo, 1e-3)
+        lb, hb = to_bits(lo), to_bits(lo + width) + 1
+        if hb - lb < 2:
+            continue
+        nb = int(rng.choice([1, 2, 256, 4096, 65536, 1 << 20]))
+        sc = _scale_for(lb, hb, nb)
+        for b in (0, 1, nb // 2, nb - 1, nb, int(rng.integers(0, nb + 1))):
+            if b == 0 and sc == float("inf"):
+                continue
+            assert bucket_lower_bits(b, lb, hb, sc, nb) == _bisect_bucket_lower_bits(b, lb, hb, sc, nb)
+            checked += 1
+    assert checked > 2000
+
+
+def test_merged_dz_windows_cover_their_members():
+    """engine._merge_dz_windows: every class keeps a window that contains its own, runs share one
+    window, the union is at most WINDOW_MERGE_GROWTH times the widest member, full-range windows
+    are left alone."""
+    from skgstat_b200.engine import PairEngine
+    full = to_bits(9.0) + 1
+    lo_v = np.array([0.20, 0.46, 0.73, 0.0, 1.38, 1.42, 1.43, 1.41, 1.45, 1.47, 0.0, 1.40])
+    hi_v = np.array([0.23, 0.51, 0.81, 9.0, 1.53, 1.58, 1.60, 1.58, 1.62, 1.65, 9.0, 1.57])
+    w_lo = np.array([to_bits(x) for x in lo_v], dtype=np.uint64)
+    w_hi = np.array([to_bits(x) + 1 for x in hi_v], dtype=np.uint64)
+    w_hi[[3, 10]] = full
+    m_lo, m_hi = PairEngine._merge_dz_windows(w_lo, w_hi, full)
+    assert np.all(m_lo <= w_lo) and np.all(m_hi >= w_hi)
+    assert (m_lo[3], m_hi[3]) == (0, full) and (m_lo[10], m_hi[10]) == (0, full)
+    assert len({(int(a), int(b)) for a, b in zip(m_lo[4:10], m_hi[4:10])}) == 1      # one run
+    assert (int(m_lo[0]), int(m_hi[0])) == (int(w_lo[0]), int(w_hi[0]))             # distinct medians stay apart
+    widths = hi_v - lo_v
+    for g in (4, 5, 6, 7, 8, 9):
+        assert from_bits(int(m_hi[g])) - from_bits(int(m_lo[g])) <= PairEngine.WINDOW_MERGE_GROWTH * widths[4:10].max() + 1e-12
+    assert (int(m_lo[11]), int(m_hi[11])) == (int(w_lo[11]), int(w_hi[11]))         # a full-range class breaks the run
