@@ -47,7 +47,7 @@ UNIT = "pairs/s"
 N_LAGS = 25
 # FP64 operations per pair (2-D): 3 sub + 3 mul + 2 add + 1 sqrt-equivalent for
 # matheron; cressie adds sqrt|dz| and its accumulate; the directional mask ~6 mul/add
-FLOPS = {"matheron": 9.0, "cressie": 11.0, "directional": 15.0}
+FLOPS = {"matheron": 9.0, "cressie": 11.0, "directional": 15.0, "dowd": 6.0}
 C3 = dict(n=200000, extent=10000.0, corr=1000.0, seed=0)
 C2 = dict(n=20000, extent=1000.0, corr=100.0, seed=0)
 C4 = dict(n=100000, extent=10000.0, corr=800.0, seed=4)
@@ -297,6 +297,44 @@ def fused_leg(X, c, v, estimator, steps, warmup, edges=None, dirp=None):
     return step_ms, kern_ms, (kept, cand, slots, int(ctr[4])), launches, (cnt, ssq, srt)
 
 
+def dowd_sweep_leg(X, c, v, edges, steps):
+    """Device time of the dominant kernel of the Dowd path: skg_pair_dz_windows (per-lag pair count,
+    count below the lag's median window, in-window |dz| histogram) with the windows the engine
+    derives from its sub-sample.  Returns (kernel ms, in-window share of the in-range pairs)."""
+    import torch
+    from skgstat_b200._exact import sq_threshold_bits, to_bits
+    from skgstat_b200.engine import PairEngine, _hptr, _ptr
+    from skgstat_b200.select import _scale_for
+    eng = PairEngine(c, v, group=X.group)
+    thr = sq_threshold_bits(edges)
+    nl, nbk = len(edges), 1 << 12
+    hi = to_bits(eng._dz_bound) + 1
+    w_lo, w_hi = eng._merge_dz_windows(*eng._median_windows(thr, None, hi), hi)
+    sc = np.array([_scale_for(int(a), int(b), nbk) if b > a else 0.0 for a, b in zip(w_lo, w_hi)])
+    cnt = torch.zeros(nl, dtype=torch.int64, device="cuda")
+    below = torch.zeros(nl, dtype=torch.float64, device="cuda")
+    hist = torch.zeros(nl * nbk, dtype=torch.int64, device="cuda")
+    scratch = eng._hist_scratch(nl)
+    evs = []
+    for i in range(3 + steps):
+        X.flush.zero_()
+        cnt.zero_(); below.zero_(); hist.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = X.lib.skg_pair_dz_windows(_ptr(eng.coords), _ptr(eng.values), 1, 0, eng.n, eng.dim, None, _hptr(thr),
+                                       nl, _hptr(w_lo), _hptr(w_hi), _hptr(sc), nbk, _ptr(cnt), _ptr(below),
+                                       _ptr(hist), _ptr(scratch), scratch.numel(), eng.t0, eng.t1, eng.tstride,
+                                       eng._stream())
+        e1.record()
+        assert rc == 0
+        if i >= 3:
+            evs.append((e0, e1))
+    X.barrier()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    inside = float(hist.sum().item()) / max(float(cnt.sum().item()), 1.0)
+    return ms, inside, float(cnt.sum().item())
+
+
 def e2e_leg(X, make, steps, warm=3):
     """Wall time of the public call with host buffers (H2D + D2H inside), max over ranks."""
     import torch
@@ -371,8 +409,10 @@ def run_own(args):
 
     X.barrier, X.max_over_ranks = barrier, max_over_ranks
     pk_ms, pk_fma = C.c_double(), C.c_double()
-    _lib.check(X.lib.skg_fp64_peak(4096, C.byref(pk_ms), C.byref(pk_fma)), "skg_fp64_peak")
-    X.peak_tflops = 2.0 * pk_fma.value / (pk_ms.value * 1e-3) / 1e12
+    X.peak_tflops = 0.0
+    for _ in range(4):   # the first probe can run while the clocks still ramp up: the best of four is the peak
+        _lib.check(X.lib.skg_fp64_peak(4096, C.byref(pk_ms), C.byref(pk_fma)), "skg_fp64_peak")
+        X.peak_tflops = max(X.peak_tflops, 2.0 * pk_fma.value / (pk_ms.value * 1e-3) / 1e12)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -424,6 +464,8 @@ def run_own(args):
     ed_s, dh2d, dd2h, _ = e2e_leg(
         X, lambda: skg.Variogram(c3, v3, estimator="dowd", n_lags=N_LAGS, maxlag="median",
                                  fit_method=None, process_group=X.group).experimental, 5, warm=3)
+    dk_ms, d_inside, d_pairs = dowd_sweep_leg(X, c3, v3, edges3, 3)
+    dk_ms = max_over_ranks(dk_ms)
     if rank == 0:
         out["config3_matheron"] = {
             "value": pairs3 / (sm * 1e-3), "unit": UNIT, "ms_per_step": sm,
@@ -434,7 +476,19 @@ def run_own(args):
             "e2e": {"value": pairs3 / ed_s, "unit": UNIT, "ms_per_step": ed_s * 1e3,
                     "h2d_bytes_per_step": int(dh2d), "d2h_bytes_per_step": int(dd2h),
                     "call": "Variogram(coords, values, 'dowd', n_lags=25, maxlag='median').experimental"},
-            "note": "per-lag exact median of |dz| (select sweeps), no single fused kernel to quote"}
+            "roofline": {
+                "bound": "fp64", "kernel": "pair_hist_win_kernel<4,1> (skg_pair_dz_windows: per-lag count, count "
+                                           "below the median window, in-window |dz| histogram)",
+                "kernel_ms": dk_ms, "flops_per_pair": FLOPS["dowd"],
+                "achieved": FLOPS["dowd"] * d_pairs / (dk_ms * 1e-3) / 1e12, "peak": X.peak_tflops,
+                "unit": "TFLOP/s", "frac": FLOPS["dowd"] * d_pairs / (dk_ms * 1e-3) / 1e12 / X.peak_tflops,
+                "traffic": 6.7e6, "in_window_share": d_inside,
+                "fp64_pipe_pct": 34.7, "issue_active_pct": 62.1,
+                "from": "profiles/r2_pair_dz_windows_ncu_summary.txt (N=200k, 21.75 ms under ncu)",
+                "note": "compare-bound, not flop-bound: 6 FP64 arithmetic + 4 FP64 compares per pair, ~15 integer / "
+                        "predicate instructions; achieved counts the in-range pairs (the per-lag counts) only; the second "
+                        "kernel of the path is pair_dz_gather_kernel (8.8 ms, profiles/r2_pair_dz_gather_ncu_summary.txt)"},
+            "note": "per-lag exact median of |dz|: sub-sample windows, one counting sweep, one gather"}
 
     # ---------------------------------------------------------------- config 2 (single-GPU quote)
     c2, v2 = make_inputs(**C2)
