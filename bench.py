@@ -47,7 +47,7 @@ UNIT = "pairs/s"
 N_LAGS = 25
 # FP64 operations per pair (2-D): 3 sub + 3 mul + 2 add + 1 sqrt-equivalent for
 # matheron; cressie adds sqrt|dz| and its accumulate; the directional mask ~6 mul/add
-FLOPS = {"matheron": 9.0, "cressie": 11.0, "directional": 15.0, "dowd": 6.0}
+FLOPS = {"matheron": 9.0, "cressie": 11.0, "directional": 15.0, "dowd": 8.0}
 C3 = dict(n=200000, extent=10000.0, corr=1000.0, seed=0)
 C2 = dict(n=20000, extent=1000.0, corr=100.0, seed=0)
 C4 = dict(n=100000, extent=10000.0, corr=800.0, seed=4)
@@ -485,7 +485,7 @@ def run_own(args):
                 "traffic": 6.7e6, "in_window_share": d_inside,
                 "fp64_pipe_pct": 34.7, "issue_active_pct": 62.1,
                 "from": "profiles/r2_pair_dz_windows_ncu_summary.txt (N=200k, 21.75 ms under ncu)",
-                "note": "compare-bound, not flop-bound: 6 FP64 arithmetic + 4 FP64 compares per pair, ~15 integer / "
+                "note": "SURVEY 8(d): 8 ops per pair for the dowd sweep; compare-bound, not flop-bound: 6 FP64 arithmetic + 4 FP64 compares per pair, ~15 integer / "
                         "predicate instructions; achieved counts the in-range pairs (the per-lag counts) only; the second "
                         "kernel of the path is pair_dz_gather_kernel (8.8 ms, profiles/r2_pair_dz_gather_ncu_summary.txt)"},
             "note": "per-lag exact median of |dz|: sub-sample windows, one counting sweep, one gather"}
