@@ -96,3 +96,17 @@ def test_no_cpu_fallback_without_cuda():
     import skgstat_b200 as skg
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         skg.Variogram(np.random.rand(10, 2), np.random.rand(10))
+
+
+def test_makefile_builds_every_cuda_source():
+    """build() runs `make -C scikit-gstat_b200/csrc`: a kernel file missing from SRC would compile
+    nowhere and only show up as an undefined symbol on the GPU box."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "scikit-gstat_b200", "csrc")
+    text = open(os.path.join(csrc, "Makefile")).read()
+    listed = set(re.search(r"^SRC\s*:=\s*(.+)$", text, re.M).group(1).split())
+    present = {os.path.basename(p) for p in glob.glob(os.path.join(csrc, "*.cu"))}
+    assert listed == present
